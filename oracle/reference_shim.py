@@ -1,0 +1,109 @@
+"""TEST INFRASTRUCTURE -- never imported by the product package.
+
+Loads the UNMODIFIED reference `/root/reference/audio_search.py` in this build container so its
+own `search_with_fusion` (audio_search.py:624-699) and `_analyze_query_for_weights` (:457-622)
+can be executed on chosen inputs.  Used only to (1) pin the numpy restatement in
+`oracle/numpy_oracle.py` and (2) mint the golden fixtures under `tests/golden/`
+(`oracle/make_golden.py`).  `/root/reference` does not exist on the GPU box; nothing marked
+`gpu`, `smoke()` or `bench.py` may call this.
+
+The reference imports streamlit / librosa / sentence_transformers at module top
+(audio_search.py:7,9,12).  None is installed and none is touched by the two functions we run, so
+they are replaced by empty stub modules.  `transformers` must be imported BEFORE the stubs exist
+(it probes `librosa.__spec__`), see SURVEY.md Appendix A.
+"""
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+
+REFERENCE_FILE = os.environ.get("CAB_REFERENCE_FILE", "/root/reference/audio_search.py")
+
+
+def available() -> bool:
+    return os.path.exists(REFERENCE_FILE)
+
+
+_module = None
+
+
+def load():
+    """Import the reference module once (stubbing the three absent third-party packages)."""
+    global _module
+    if _module is not None:
+        return _module
+    if not available():
+        raise FileNotFoundError(REFERENCE_FILE)
+    from transformers import pipeline, WhisperProcessor, WhisperForConditionalGeneration  # noqa: F401
+    for name in ("streamlit", "librosa", "sentence_transformers"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    if not hasattr(sys.modules["sentence_transformers"], "SentenceTransformer"):
+        sys.modules["sentence_transformers"].SentenceTransformer = object
+    spec = importlib.util.spec_from_file_location("reference_audio_search", REFERENCE_FILE)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    _module = mod
+    return mod
+
+
+class FakeEmbedder:
+    """Stands in for SentenceTransformer: `.encode(text)` returns the vector registered for it."""
+
+    def __init__(self, table: dict[str, np.ndarray]):
+        self.table = {k: np.asarray(v, dtype=np.float32) for k, v in table.items()}
+
+    def encode(self, text, **_kw):
+        return self.table[text].copy()
+
+
+def make_segment(i: int, asr_emb, audio_emb, asr_success=None, audio_success=None) -> dict:
+    """A segment record with the reference's 12 keys (audio_search.py:275-294)."""
+    asr_success = (asr_emb is not None) if asr_success is None else asr_success
+    audio_success = (audio_emb is not None) if audio_success is None else audio_success
+    return {
+        "segment_id": f"seg_{i}",
+        "start_time": 10.0 * i,
+        "end_time": 10.0 * i + 10.0,
+        "duration": 10.0,
+        "asr_text": f"asr text {i}" if asr_success else "",
+        "asr_embedding": None if asr_emb is None else np.asarray(asr_emb, dtype=np.float32),
+        "asr_success": bool(asr_success),
+        "audio_description": f"audio description {i}" if audio_success else "",
+        "audio_embedding": None if audio_emb is None else np.asarray(audio_emb, dtype=np.float32),
+        "audio_success": bool(audio_success),
+        "audio_data": None,
+        "sample_rate": 16000,
+    }
+
+
+def segments_from_arrays(asr, audio, flags, has_asr=None, has_audio=None) -> list[dict]:
+    """Build the reference's list-of-dict library from row matrices + success flags.
+    By default an embedding is present iff its pipeline succeeded (audio_search.py:282-289)."""
+    n = len(flags)
+    segs = []
+    for i in range(n):
+        sa, sb = bool(flags[i] & 1), bool(flags[i] & 2)
+        ha = sa if has_asr is None else bool(has_asr[i])
+        hb = sb if has_audio is None else bool(has_audio[i])
+        segs.append(make_segment(i, asr[i] if ha else None, audio[i] if hb else None, sa, sb))
+    return segs
+
+
+def reference_engine(segments: list[dict], queries: dict[str, np.ndarray]):
+    """A reference `DualPipelineAudioSearch` holding `segments`, with query text -> vector."""
+    ref = load()
+    eng = ref.DualPipelineAudioSearch()
+    eng.text_embedder = FakeEmbedder(queries)
+    eng.audio_segments = segments
+    return eng
+
+
+def reference_weights(query: str):
+    ref = load()
+    eng = ref.DualPipelineAudioSearch.__new__(ref.DualPipelineAudioSearch)
+    return eng._analyze_query_for_weights(query)
