@@ -1,0 +1,162 @@
+/*
+ * cab.h -- C-ABI of the B200-native fused dual-corpus retrieval engine ("cab" = ClipABit).
+ *
+ * Drop-in boundary for ONE path of ClipABit/Multimodal-Audio-Search:
+ *   DualPipelineAudioSearch.search_with_fusion        /root/reference/audio_search.py:624-699
+ * minus the query-embedding call (:635) and the keyword weight rule (:457-622), which stay on
+ * the host.  The reference has no FFI/plugin interface (it is one Python file); each entry point
+ * below names the reference statement(s) it replaces.  The Python side that mirrors the
+ * reference's call surface is multimodal_audio_search_b200/engine.py; the binding a maintainer
+ * would add to the reference is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C types only; every function returns a cab_status (0 = ok) and never throws;
+ *   - cab_last_error(idx) returns a static/handle-owned message for the last failure;
+ *   - a handle is externally synchronised (one caller at a time); distinct handles may be used
+ *     from distinct threads (the reference keeps one engine per Streamlit session, :708-711);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the handle's own stream);
+ *   - `*_loc` says where a caller buffer lives: CAB_HOST or CAB_DEVICE;
+ *   - there is NO CPU fallback: without a usable CUDA device every call fails with
+ *     CAB_ERR_NO_DEVICE.
+ */
+#ifndef CAB_H_
+#define CAB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define CAB_API __attribute__((visibility("default")))
+#else
+#define CAB_API
+#endif
+
+#define CAB_VERSION 100          /* 0.1.0 */
+#define CAB_DIM 384              /* all-MiniLM-L6-v2, audio_search.py:92 */
+#define CAB_MAX_K 128            /* reference uses 10 (:699); BASELINE configs use up to 100 */
+#define CAB_MAX_QUERIES 4096     /* per cab_search call */
+
+typedef struct cab_index cab_index;
+
+typedef enum cab_status {
+    CAB_OK = 0,
+    CAB_ERR_INVALID = 1,      /* bad argument */
+    CAB_ERR_CUDA = 2,         /* a CUDA call failed (sticky on the handle) */
+    CAB_ERR_NONFINITE = 3,    /* NaN/Inf in rows or query: sklearn raises ValueError here */
+    CAB_ERR_NO_DEVICE = 4,    /* no CUDA device / not an sm_100 part */
+    CAB_ERR_NOMEM = 5
+} cab_status;
+
+typedef enum cab_dtype { CAB_F32 = 0, CAB_BF16 = 1 } cab_dtype;      /* storage type of rows */
+typedef enum cab_loc { CAB_HOST = 0, CAB_DEVICE = 1 } cab_loc;
+typedef enum cab_path {                                              /* which scan kernel */
+    CAB_PATH_AUTO = 0,       /* GEMV for few queries, tensor-core GEMM for >= 64 (bf16 only) */
+    CAB_PATH_GEMV = 1,       /* HBM-bound fused GEMV + top-k (CUDA cores, fp32 accumulate) */
+    CAB_PATH_GEMM = 2        /* tcgen05/TMEM GEMM with fused weighting/top-k epilogue (bf16) */
+} cab_path;
+
+/* Row flags: the reference's per-segment `asr_success` / `audio_success` (:284, :289), which
+ * select the effective weights (:656-664).  A missing embedding (`None`, :640-651) is passed
+ * as an all-zero row: its cosine is exactly 0.0 like the reference's. */
+#define CAB_FLAG_ASR 1u
+#define CAB_FLAG_AUDIO 2u
+
+CAB_API int cab_version(void);
+CAB_API const char *cab_status_string(int status);
+/* Last error text of `idx` (or of the calling thread's last failed create when idx == NULL). */
+CAB_API const char *cab_last_error(const cab_index *idx);
+/* Number of visible CUDA devices (0 if none / driver missing). Never fails. */
+CAB_API int cab_device_count(void);
+
+/* ---- segment store: replaces the `audio_segments` list as the thing that is scanned --------
+ * (audio_search.py:115; rows appended at :797).  Two row-major [rows x 384] matrices (ASR,
+ * audio), L2-normalised on ingest, 128-byte-aligned rows, plus one flag byte per row. */
+CAB_API int cab_index_create(int dim, int dtype, int64_t capacity_rows, int device, cab_index **out);
+CAB_API int cab_index_destroy(cab_index *idx);
+CAB_API int cab_index_reserve(cab_index *idx, int64_t capacity_rows);
+CAB_API int64_t cab_index_size(const cab_index *idx);
+CAB_API int64_t cab_index_capacity(const cab_index *idx);
+CAB_API int cab_index_dtype(const cab_index *idx);
+CAB_API int cab_index_device(const cab_index *idx);
+/* Global segment index of local row 0 (corpus sharded by segment over ranks, default 0). */
+CAB_API int cab_index_set_row_base(cab_index *idx, int64_t row_base);
+CAB_API int64_t cab_index_row_base(const cab_index *idx);
+CAB_API int cab_index_clear(cab_index *idx);
+
+/* Append n_rows segments.  asr_rows / audio_rows: fp32 [n_rows x dim], raw (any length; the
+ * engine normalises like sklearn `normalize`, zero rows stay zero) or NULL (= all rows missing);
+ * flags: n_rows bytes of CAB_FLAG_* or NULL (= both pipelines succeeded).
+ * Fails with CAB_ERR_NONFINITE (nothing appended) if any value is NaN/Inf.
+ * Replaces: audio_segments.extend(...) at :797 + the per-call normalize(Y) of :646/:651. */
+CAB_API int cab_index_append(cab_index *idx, const float *asr_rows, const float *audio_rows,
+                     const uint8_t *flags, int64_t n_rows, int rows_loc, void *stream);
+
+/* Append global rows [r0, r1) of the deterministic synthetic library (seed, n_total rows,
+ * planted neighbours, optional partial flags) generated ON DEVICE; bit-identical to
+ * multimodal_audio_search_b200/synth.py.  Benchmark/test data source (BASELINE.json configs). */
+CAB_API int cab_index_append_synth(cab_index *idx, uint32_t seed, int64_t n_total, int64_t r0, int64_t r1,
+                           int n_queries, int plants, int partial, void *stream);
+/* Raw synthetic query vectors [q0, q1) as fp32 [n x dim] into `out` (host or device). */
+CAB_API int cab_synth_queries(int device, uint32_t seed, int q0, int q1, float *out, int out_loc);
+
+/* Copy normalised rows [r0, r1) back as fp32 (bf16 storage is widened) -- test/debug hook. */
+CAB_API int cab_index_read_rows(cab_index *idx, int corpus /*0 asr, 1 audio*/, int64_t r0, int64_t r1,
+                        float *out, int out_loc);
+
+/* ---- search: replaces the per-segment loop, threshold, sort and [:k]  (:639-685, :699) -------
+ * queries : fp32 [n_queries x dim], raw (re-normalised like normalize(X) at :646);
+ * w_asr, w_audio : host arrays [n_queries] of the query weights from
+ *                  _analyze_query_for_weights (:632), float64 like the reference's floats;
+ * k <= CAB_MAX_K; threshold: the reference's 0.1 (:672), strict `>` evaluated in float64.
+ * Outputs (each [n_queries x k], may be NULL if not wanted; host or device per out_loc):
+ *   out_index  global segment index, best first (score desc, index asc = Python's stable
+ *              sort, :685); -1 beyond out_count[q]
+ *   out_fusion float64 fusion_score  = eff_w_asr*asr_sim + eff_w_audio*audio_sim  (:667-670)
+ *   out_asr / out_audio  float32 cosine similarities (:646, :651)
+ *   out_flags  the row's CAB_FLAG_* byte (gives the effective weights of :656-664)
+ *   out_count  [n_queries] number of results (< k when fewer rows pass the threshold). */
+CAB_API int cab_search(cab_index *idx, const float *queries, int queries_loc, const double *w_asr,
+               const double *w_audio, int n_queries, int k, double threshold, int path,
+               int64_t *out_index, double *out_fusion, float *out_asr, float *out_audio,
+               uint8_t *out_flags, int32_t *out_count, int out_loc, void *stream);
+
+/* ---- sharded search (corpus split by segment over ranks) ----------------------------------
+ * Step 1, per rank: local top-k as packed candidates (cab_candidate[n_queries x k], device).
+ * Step 2, host plumbing: all-gather the candidate blocks of all ranks (NCCL over NVLink).
+ * Step 3, per rank: merge world x k candidates per query into the final top-k. */
+typedef struct cab_candidate {
+    int64_t index;       /* global segment index, -1 = empty slot */
+    float asr_sim;
+    float audio_sim;
+    uint32_t flags;
+    uint32_t pad;
+} cab_candidate;         /* 24 bytes */
+
+CAB_API int cab_search_candidates(cab_index *idx, const float *queries, int queries_loc,
+                          const double *w_asr, const double *w_audio, int n_queries, int k,
+                          double threshold, int path, cab_candidate *out_device, void *stream);
+CAB_API int cab_merge_candidates(cab_index *idx, const cab_candidate *cands_device, int n_lists,
+                         int n_queries, int k, const double *w_asr, const double *w_audio,
+                         double threshold, int64_t *out_index, double *out_fusion, float *out_asr,
+                         float *out_audio, uint8_t *out_flags, int32_t *out_count, int out_loc,
+                         void *stream);
+
+/* ---- tuning / introspection -------------------------------------------------------------- */
+/* Options: "gemv_variant" (0 = LDG register pipeline, 1 = TMA bulk smem ring),
+ * "gemv_blocks_per_sm", "gemv_unroll", "sync_after_search" ... ; unknown keys fail. */
+CAB_API int cab_index_set_option(cab_index *idx, const char *key, int64_t value);
+CAB_API int64_t cab_index_get_option(const cab_index *idx, const char *key);
+/* Kernels launched by this handle since creation (for bench.py's gpu_launches). */
+CAB_API int64_t cab_index_launch_count(const cab_index *idx);
+/* Device time (ms, CUDA events on the handle's stream) of the scan kernel of the last search
+ * when option "time_kernels" is 1; < 0 if not recorded. */
+CAB_API double cab_index_last_scan_ms(const cab_index *idx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAB_H_ */

@@ -1,0 +1,656 @@
+// C-ABI of the engine (include/cab.h): device-resident segment store + search orchestration.
+// No CPU fallback anywhere: if CUDA is unusable every entry point reports CAB_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "cab_internal.h"
+
+using namespace cab;
+
+namespace cab {
+// tensor-core path (cab_gemm_tc.cu)
+struct GemmScanArgs;
+int gemm_partials_per_query(int sm_count);
+bool gemm_path_available();
+void launch_gemm_scan(const ScanArgs &a, int sm_count, void *workspace, size_t workspace_bytes,
+                      cudaStream_t s, std::string *err);
+size_t gemm_workspace_bytes(int n_queries, int k, int sm_count);
+}  // namespace cab
+
+static thread_local std::string g_last_error;
+
+struct cab_index {
+    int device = 0;
+    int dtype = CAB_F32;
+    int sm_count = 148;
+    int64_t capacity = 0, size = 0, row_base = 0;
+    void *asr = nullptr, *audio = nullptr;
+    uint8_t *flags = nullptr;
+    cudaStream_t own_stream = nullptr;
+    // search workspace (device)
+    float *d_queries = nullptr;    size_t sz_queries = 0;   // [n_queries x 384]
+    double *d_w64 = nullptr;       size_t sz_w64 = 0;       // [2 x n_queries]
+    float *d_w32 = nullptr;        size_t sz_w32 = 0;       // [2 x n_queries]
+    uint64_t *d_partial_keys = nullptr;  size_t sz_pkeys = 0;
+    int32_t *d_partial_count = nullptr;  size_t sz_pcount = 0;
+    cab_candidate *d_cands = nullptr;    size_t sz_cands = 0;
+    uint8_t *d_out = nullptr;      size_t d_out_bytes = 0;  // packed outputs
+    uint8_t *d_gemm_ws = nullptr;  size_t d_gemm_ws_bytes = 0;
+    int *d_nonfinite = nullptr;
+    // pinned host staging
+    uint8_t *h_in = nullptr;  size_t h_in_bytes = 0;
+    uint8_t *h_out = nullptr; size_t h_out_bytes = 0;
+    uint8_t *h_rows = nullptr; size_t h_rows_bytes = 0;
+    float *d_rows = nullptr;  size_t d_rows_bytes = 0;   // raw-row device staging (append)
+    cudaEvent_t ev_in = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    bool ev_in_pending = false, timed = false;
+    // options
+    GemvConfig gemv{0, 0, 0};
+    int64_t opt_time_kernels = 0, opt_sync = 0, opt_gemm_min_queries = 64, opt_gemv_batch = 32;
+    int64_t launches = 0;
+    std::string err;
+    int sticky = CAB_OK;
+};
+
+static int fail(cab_index *idx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (idx) { idx->err = buf; if (code == CAB_ERR_CUDA) idx->sticky = code; }
+    g_last_error = buf;
+    return code;
+}
+
+#define CU(idx, expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(idx, e_ == cudaErrorMemoryAllocation ? CAB_ERR_NOMEM : CAB_ERR_CUDA,   \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define CHECK_HANDLE(idx)                                                        \
+    do {                                                                         \
+        if (!(idx)) return fail(nullptr, CAB_ERR_INVALID, "null index handle");  \
+        if ((idx)->sticky != CAB_OK) return (idx)->sticky;                       \
+    } while (0)
+
+static size_t elem_size(int dtype) { return dtype == CAB_BF16 ? 2 : 4; }
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int cab_version(void) { return CAB_VERSION; }
+
+const char *cab_status_string(int s) {
+    switch (s) {
+        case CAB_OK: return "ok";
+        case CAB_ERR_INVALID: return "invalid argument";
+        case CAB_ERR_CUDA: return "CUDA error";
+        case CAB_ERR_NONFINITE: return "input contains NaN or infinity";
+        case CAB_ERR_NO_DEVICE: return "no usable CUDA device (sm_100 required; there is no CPU fallback)";
+        case CAB_ERR_NOMEM: return "out of device memory";
+        default: return "unknown status";
+    }
+}
+
+const char *cab_last_error(const cab_index *idx) { return idx ? idx->err.c_str() : g_last_error.c_str(); }
+
+int cab_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+static int grow(cab_index *idx, int64_t new_cap) {
+    if (new_cap <= idx->capacity) return CAB_OK;
+    const size_t row_bytes = CAB_DIM * elem_size(idx->dtype);
+    void *na = nullptr, *nb = nullptr;
+    uint8_t *nf = nullptr;
+    CU(idx, cudaSetDevice(idx->device));
+    cudaError_t e = cudaMalloc(&na, size_t(new_cap) * row_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&nb, size_t(new_cap) * row_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&nf, size_t(new_cap));
+    if (e != cudaSuccess) {
+        cudaFree(na); cudaFree(nb); cudaFree(nf); cudaGetLastError();
+        return fail(idx, CAB_ERR_NOMEM, "cannot allocate %lld rows (%s)", (long long)new_cap, cudaGetErrorString(e));
+    }
+    if (idx->size > 0) {
+        CU(idx, cudaMemcpyAsync(na, idx->asr, size_t(idx->size) * row_bytes, cudaMemcpyDeviceToDevice, idx->own_stream));
+        CU(idx, cudaMemcpyAsync(nb, idx->audio, size_t(idx->size) * row_bytes, cudaMemcpyDeviceToDevice, idx->own_stream));
+        CU(idx, cudaMemcpyAsync(nf, idx->flags, size_t(idx->size), cudaMemcpyDeviceToDevice, idx->own_stream));
+    }
+    CU(idx, cudaStreamSynchronize(idx->own_stream));
+    cudaFree(idx->asr); cudaFree(idx->audio); cudaFree(idx->flags);
+    idx->asr = na; idx->audio = nb; idx->flags = nf; idx->capacity = new_cap;
+    return CAB_OK;
+}
+
+int cab_index_create(int dim, int dtype, int64_t capacity_rows, int device, cab_index **out) {
+    if (!out) return fail(nullptr, CAB_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (dim != CAB_DIM) return fail(nullptr, CAB_ERR_INVALID, "dim must be %d (all-MiniLM-L6-v2), got %d", CAB_DIM, dim);
+    if (dtype != CAB_F32 && dtype != CAB_BF16) return fail(nullptr, CAB_ERR_INVALID, "dtype must be CAB_F32 or CAB_BF16");
+    if (capacity_rows < 0 || capacity_rows > 0xFFFFFFF0ll) return fail(nullptr, CAB_ERR_INVALID, "capacity_rows out of range");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(nullptr, CAB_ERR_NO_DEVICE, "no CUDA device visible; this engine has no CPU fallback");
+    }
+    if (device < 0 || device >= n) return fail(nullptr, CAB_ERR_INVALID, "device %d out of range (%d visible)", device, n);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { cudaGetLastError(); return fail(nullptr, CAB_ERR_NO_DEVICE, "cannot query device %d", device); }
+    if (prop.major != 10) return fail(nullptr, CAB_ERR_NO_DEVICE, "device %d is sm_%d%d; kernels are built for sm_100a only", device, prop.major, prop.minor);
+    cab_index *idx = new (std::nothrow) cab_index();
+    if (!idx) return fail(nullptr, CAB_ERR_NOMEM, "host allocation failed");
+    idx->device = device; idx->dtype = dtype; idx->sm_count = prop.multiProcessorCount;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&idx->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&idx->d_nonfinite, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(idx->d_nonfinite, 0, sizeof(int));
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&idx->ev_in, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreate(&idx->ev_t0);
+    if (e == cudaSuccess) e = cudaEventCreate(&idx->ev_t1);
+    if (e != cudaSuccess) {
+        int rc = fail(nullptr, CAB_ERR_CUDA, "index setup failed: %s", cudaGetErrorString(e));
+        cab_index_destroy(idx);
+        return rc;
+    }
+    if (capacity_rows > 0) {
+        int rc = grow(idx, capacity_rows);
+        if (rc != CAB_OK) { g_last_error = idx->err; cab_index_destroy(idx); return rc; }
+    }
+    *out = idx;
+    return CAB_OK;
+}
+
+int cab_index_destroy(cab_index *idx) {
+    if (!idx) return CAB_OK;
+    cudaSetDevice(idx->device);
+    if (idx->own_stream) cudaStreamSynchronize(idx->own_stream);
+    cudaFree(idx->asr); cudaFree(idx->audio); cudaFree(idx->flags);
+    cudaFree(idx->d_queries); cudaFree(idx->d_w64); cudaFree(idx->d_w32);
+    cudaFree(idx->d_partial_keys); cudaFree(idx->d_partial_count); cudaFree(idx->d_cands);
+    cudaFree(idx->d_out); cudaFree(idx->d_gemm_ws); cudaFree(idx->d_nonfinite); cudaFree(idx->d_rows);
+    cudaFreeHost(idx->h_in); cudaFreeHost(idx->h_out); cudaFreeHost(idx->h_rows);
+    if (idx->ev_in) cudaEventDestroy(idx->ev_in);
+    if (idx->ev_t0) cudaEventDestroy(idx->ev_t0);
+    if (idx->ev_t1) cudaEventDestroy(idx->ev_t1);
+    if (idx->own_stream) cudaStreamDestroy(idx->own_stream);
+    cudaGetLastError();
+    delete idx;
+    return CAB_OK;
+}
+
+int cab_index_reserve(cab_index *idx, int64_t capacity_rows) {
+    CHECK_HANDLE(idx);
+    if (capacity_rows > 0xFFFFFFF0ll) return fail(idx, CAB_ERR_INVALID, "capacity_rows out of range");
+    return grow(idx, capacity_rows);
+}
+int64_t cab_index_size(const cab_index *idx) { return idx ? idx->size : -1; }
+int64_t cab_index_capacity(const cab_index *idx) { return idx ? idx->capacity : -1; }
+int cab_index_dtype(const cab_index *idx) { return idx ? idx->dtype : -1; }
+int cab_index_device(const cab_index *idx) { return idx ? idx->device : -1; }
+int cab_index_set_row_base(cab_index *idx, int64_t row_base) {
+    CHECK_HANDLE(idx);
+    if (row_base < 0) return fail(idx, CAB_ERR_INVALID, "row_base must be >= 0");
+    idx->row_base = row_base;
+    return CAB_OK;
+}
+int64_t cab_index_row_base(const cab_index *idx) { return idx ? idx->row_base : -1; }
+int cab_index_clear(cab_index *idx) { CHECK_HANDLE(idx); idx->size = 0; return CAB_OK; }
+
+static int ensure_pinned(cab_index *idx, uint8_t **p, size_t *have, size_t want) {
+    if (*have >= want) return CAB_OK;
+    if (*p) { cudaFreeHost(*p); *p = nullptr; *have = 0; }
+    want = align_up(want, 4096);
+    CU(idx, cudaMallocHost((void **)p, want));
+    *have = want;
+    return CAB_OK;
+}
+
+static int check_nonfinite(cab_index *idx, cudaStream_t s, bool *bad) {
+    int h = 0;
+    CU(idx, cudaMemcpyAsync(&h, idx->d_nonfinite, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(idx, cudaStreamSynchronize(s));
+    *bad = h != 0;
+    if (h) { CU(idx, cudaMemsetAsync(idx->d_nonfinite, 0, sizeof(int), s)); CU(idx, cudaStreamSynchronize(s)); }
+    return CAB_OK;
+}
+
+int cab_index_append(cab_index *idx, const float *asr_rows, const float *audio_rows,
+                     const uint8_t *flags, int64_t n_rows, int rows_loc, void *stream) {
+    CHECK_HANDLE(idx);
+    if (n_rows < 0) return fail(idx, CAB_ERR_INVALID, "n_rows < 0");
+    if (n_rows == 0) return CAB_OK;
+    if (rows_loc != CAB_HOST && rows_loc != CAB_DEVICE) return fail(idx, CAB_ERR_INVALID, "rows_loc");
+    if (idx->size + n_rows > 0xFFFFFFF0ll) return fail(idx, CAB_ERR_INVALID, "more than 2^32 rows per index");
+    CU(idx, cudaSetDevice(idx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : idx->own_stream;
+    if (idx->size + n_rows > idx->capacity) {
+        int rc = grow(idx, std::max(idx->size + n_rows, idx->capacity * 2));
+        if (rc != CAB_OK) return rc;
+    }
+    const int64_t dst0 = idx->size;
+    if (rows_loc == CAB_DEVICE) {
+        launch_normalize_rows(asr_rows, idx->asr, idx->dtype, dst0, n_rows, idx->d_nonfinite, s);
+        launch_normalize_rows(audio_rows, idx->audio, idx->dtype, dst0, n_rows, idx->d_nonfinite, s);
+        idx->launches += 2;
+        if (flags) CU(idx, cudaMemcpyAsync(idx->flags + dst0, flags, size_t(n_rows), cudaMemcpyDeviceToDevice, s));
+        else CU(idx, cudaMemsetAsync(idx->flags + dst0, 3, size_t(n_rows), s));
+    } else {
+        const int64_t chunk = 16384;                                   // rows per staging step (2 x 24 MB)
+        const size_t row_bytes = CAB_DIM * sizeof(float);
+        int rc = ensure_pinned(idx, &idx->h_rows, &idx->h_rows_bytes, 2 * size_t(chunk) * row_bytes);
+        if (rc != CAB_OK) return rc;
+        if (idx->d_rows_bytes < 2 * size_t(chunk) * row_bytes) {
+            cudaFree(idx->d_rows); idx->d_rows = nullptr; idx->d_rows_bytes = 0;
+            CU(idx, cudaMalloc((void **)&idx->d_rows, 2 * size_t(chunk) * row_bytes));
+            idx->d_rows_bytes = 2 * size_t(chunk) * row_bytes;
+        }
+        for (int64_t r = 0; r < n_rows; r += chunk) {
+            const int64_t m = std::min(chunk, n_rows - r);
+            float *ha = reinterpret_cast<float *>(idx->h_rows), *hb = ha + chunk * CAB_DIM;
+            float *da = idx->d_rows, *db = da + chunk * CAB_DIM;
+            if (asr_rows) { memcpy(ha, asr_rows + r * CAB_DIM, size_t(m) * row_bytes); CU(idx, cudaMemcpyAsync(da, ha, size_t(m) * row_bytes, cudaMemcpyHostToDevice, s)); }
+            if (audio_rows) { memcpy(hb, audio_rows + r * CAB_DIM, size_t(m) * row_bytes); CU(idx, cudaMemcpyAsync(db, hb, size_t(m) * row_bytes, cudaMemcpyHostToDevice, s)); }
+            launch_normalize_rows(asr_rows ? da : nullptr, idx->asr, idx->dtype, dst0 + r, m, idx->d_nonfinite, s);
+            launch_normalize_rows(audio_rows ? db : nullptr, idx->audio, idx->dtype, dst0 + r, m, idx->d_nonfinite, s);
+            idx->launches += 2;
+            CU(idx, cudaStreamSynchronize(s));                         // staging buffers are reused
+        }
+        if (flags) CU(idx, cudaMemcpyAsync(idx->flags + dst0, flags, size_t(n_rows), cudaMemcpyHostToDevice, s));
+        else CU(idx, cudaMemsetAsync(idx->flags + dst0, 3, size_t(n_rows), s));
+    }
+    CU(idx, cudaGetLastError());
+    bool bad = false;
+    int rc = check_nonfinite(idx, s, &bad);
+    if (rc != CAB_OK) return rc;
+    if (bad) return fail(idx, CAB_ERR_NONFINITE, "Input contains NaN or infinity (rows not appended)");
+    idx->size += n_rows;
+    return CAB_OK;
+}
+
+static uint32_t h_mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+    return x;
+}
+static uint64_t gcd64(uint64_t a, uint64_t b) { while (b) { uint64_t t = a % b; a = b; b = t; } return a; }
+static uint64_t modinv(uint64_t a, uint64_t m) {      // a^-1 mod m, gcd(a, m) == 1, m <= 2^32
+    __int128 t = 0, nt = 1, r = m, nr = a % m;
+    while (nr != 0) { __int128 q = r / nr; __int128 x = t - q * nt; t = nt; nt = x; x = r - q * nr; r = nr; nr = x; }
+    if (t < 0) t += m;
+    return (uint64_t)t;
+}
+// Mirror of synth.plant_spec()
+static SynthParams make_synth(uint32_t seed, int64_t n_total, int n_queries, int plants) {
+    SynthParams p{};
+    p.seed = seed; p.n_total = uint64_t(n_total); p.plants = uint32_t(plants > 0 ? plants : 1);
+    p.n_plants_total = 0; p.base = 0; p.inv_stride = 1;
+    if (n_total <= 1 || int64_t(n_queries) * plants == 0) return p;
+    uint64_t n = uint64_t(n_total);
+    uint64_t stride = uint64_t(double(n_total) * 0.6180339887) | 1ull;
+    while (gcd64(stride, n) != 1) stride += 2;
+    stride %= n;
+    if (stride == 0) stride = 1;
+    p.base = h_mix32(seed ^ 0xABCD1234u) % n;
+    p.inv_stride = modinv(stride, n);
+    p.n_plants_total = uint32_t(int64_t(n_queries) * plants);
+    return p;
+}
+
+int cab_index_append_synth(cab_index *idx, uint32_t seed, int64_t n_total, int64_t r0, int64_t r1,
+                           int n_queries, int plants, int partial, void *stream) {
+    CHECK_HANDLE(idx);
+    if (n_total <= 0 || n_total > 0xFFFFFFF0ll || r0 < 0 || r1 < r0 || r1 > n_total || n_queries < 0 || plants < 0)
+        return fail(idx, CAB_ERR_INVALID, "bad synthetic library range");
+    if (int64_t(n_queries) * plants > n_total) return fail(idx, CAB_ERR_INVALID, "more planted rows than library rows");
+    const int64_t n_rows = r1 - r0;
+    if (n_rows == 0) return CAB_OK;
+    CU(idx, cudaSetDevice(idx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : idx->own_stream;
+    if (idx->size + n_rows > idx->capacity) {
+        int rc = grow(idx, std::max(idx->size + n_rows, idx->capacity * 2));
+        if (rc != CAB_OK) return rc;
+    }
+    const SynthParams p = make_synth(seed, n_total, n_queries, plants);
+    const int64_t chunk = 65536;
+    const size_t need = size_t(chunk) * CAB_DIM * sizeof(float);
+    if (idx->d_rows_bytes < need) {
+        cudaFree(idx->d_rows); idx->d_rows = nullptr; idx->d_rows_bytes = 0;
+        CU(idx, cudaMalloc((void **)&idx->d_rows, need));
+        idx->d_rows_bytes = need;
+    }
+    for (int st = 0; st < 2; ++st) {
+        void *dst = st == 0 ? idx->asr : idx->audio;
+        for (int64_t r = 0; r < n_rows; r += chunk) {
+            const int64_t m = std::min(chunk, n_rows - r);
+            launch_synth_rows(p, st, r0 + r, m, idx->d_rows, s);
+            launch_normalize_rows(idx->d_rows, dst, idx->dtype, idx->size + r, m, idx->d_nonfinite, s);
+            idx->launches += 2;
+        }
+    }
+    launch_synth_flags(seed, partial, r0, n_rows, idx->flags + idx->size, s);
+    idx->launches += 1;
+    CU(idx, cudaGetLastError());
+    CU(idx, cudaStreamSynchronize(s));
+    idx->size += n_rows;
+    return CAB_OK;
+}
+
+int cab_synth_queries(int device, uint32_t seed, int q0, int q1, float *out, int out_loc) {
+    if (!out || q0 < 0 || q1 < q0) return fail(nullptr, CAB_ERR_INVALID, "bad query range");
+    if (q1 == q0) return CAB_OK;
+    if (cab_device_count() == 0) return fail(nullptr, CAB_ERR_NO_DEVICE, "no CUDA device visible");
+    CU(nullptr, cudaSetDevice(device));
+    SynthParams p{};
+    p.seed = seed; p.n_total = 0xFFFFFFFFull; p.n_plants_total = 0; p.plants = 1;
+    const size_t bytes = size_t(q1 - q0) * CAB_DIM * sizeof(float);
+    float *d = out;
+    if (out_loc == CAB_HOST) CU(nullptr, cudaMalloc((void **)&d, bytes));
+    launch_synth_rows(p, 2, q0, q1 - q0, d, 0);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && out_loc == CAB_HOST) e = cudaMemcpy(out, d, bytes, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (out_loc == CAB_HOST) cudaFree(d);
+    if (e != cudaSuccess) return fail(nullptr, CAB_ERR_CUDA, "synthetic queries: %s", cudaGetErrorString(e));
+    return CAB_OK;
+}
+
+int cab_index_read_rows(cab_index *idx, int corpus, int64_t r0, int64_t r1, float *out, int out_loc) {
+    CHECK_HANDLE(idx);
+    if (!out || r0 < 0 || r1 < r0 || r1 > idx->size || (corpus != 0 && corpus != 1))
+        return fail(idx, CAB_ERR_INVALID, "bad row range");
+    if (r1 == r0) return CAB_OK;
+    CU(idx, cudaSetDevice(idx->device));
+    const size_t bytes = size_t(r1 - r0) * CAB_DIM * sizeof(float);
+    float *d = out;
+    if (out_loc == CAB_HOST) CU(idx, cudaMalloc((void **)&d, bytes));
+    launch_widen_rows(corpus == 0 ? idx->asr : idx->audio, idx->dtype, r0, r1 - r0, d, idx->own_stream);
+    idx->launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && out_loc == CAB_HOST) e = cudaMemcpyAsync(out, d, bytes, cudaMemcpyDeviceToHost, idx->own_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(idx->own_stream);
+    if (out_loc == CAB_HOST) cudaFree(d);
+    if (e != cudaSuccess) return fail(idx, CAB_ERR_CUDA, "read_rows: %s", cudaGetErrorString(e));
+    return CAB_OK;
+}
+
+// ---- search ------------------------------------------------------------------------------------
+struct OutLayout {
+    size_t index, fusion, asr, audio, flags, count, nonfinite, total;
+};
+static OutLayout out_layout(int nq, int k) {
+    OutLayout L;
+    size_t o = 0;
+    L.index = o; o += align_up(size_t(nq) * k * 8, 256);
+    L.fusion = o; o += align_up(size_t(nq) * k * 8, 256);
+    L.asr = o; o += align_up(size_t(nq) * k * 4, 256);
+    L.audio = o; o += align_up(size_t(nq) * k * 4, 256);
+    L.flags = o; o += align_up(size_t(nq) * k, 256);
+    L.count = o; o += align_up(size_t(nq) * 4, 256);
+    L.nonfinite = o; o += 256;
+    L.total = o;
+    return L;
+}
+
+template <typename T>
+static int ensure_dev(cab_index *idx, T **p, size_t *have, size_t want) {
+    if (*have >= want) return CAB_OK;
+    cudaFree(*p); *p = nullptr; *have = 0;
+    want = align_up(want, 256);
+    CU(idx, cudaMalloc((void **)p, want));
+    *have = want;
+    return CAB_OK;
+}
+
+static int ensure_workspace(cab_index *idx, int nq, int k, int n_partials, int scan_batch, size_t gemm_ws) {
+    int rc;
+    if ((rc = ensure_dev(idx, &idx->d_queries, &idx->sz_queries, size_t(nq) * CAB_DIM * 4))) return rc;
+    if ((rc = ensure_dev(idx, &idx->d_w64, &idx->sz_w64, size_t(nq) * 2 * 8))) return rc;
+    if ((rc = ensure_dev(idx, &idx->d_w32, &idx->sz_w32, size_t(nq) * 2 * 4))) return rc;
+    if ((rc = ensure_dev(idx, &idx->d_partial_keys, &idx->sz_pkeys, size_t(scan_batch) * n_partials * k * 8))) return rc;
+    if ((rc = ensure_dev(idx, &idx->d_partial_count, &idx->sz_pcount, size_t(scan_batch) * n_partials * 4))) return rc;
+    if ((rc = ensure_dev(idx, &idx->d_cands, &idx->sz_cands, size_t(nq) * k * sizeof(cab_candidate)))) return rc;
+    if ((rc = ensure_dev(idx, &idx->d_out, &idx->d_out_bytes, out_layout(nq, k).total))) return rc;
+    if (gemm_ws && (rc = ensure_dev(idx, &idx->d_gemm_ws, &idx->d_gemm_ws_bytes, gemm_ws))) return rc;
+    return CAB_OK;
+}
+
+// Stage queries + weights on the device; run scan + finalize -> idx->d_cands[nq x k].
+static int run_local(cab_index *idx, const float *queries, int queries_loc, const double *w_asr,
+                     const double *w_audio, int nq, int k, double threshold, int path,
+                     cudaStream_t s) {
+    if (!queries || !w_asr || !w_audio) return fail(idx, CAB_ERR_INVALID, "queries / weights are null");
+    if (nq <= 0 || nq > CAB_MAX_QUERIES) return fail(idx, CAB_ERR_INVALID, "n_queries must be in 1..%d", CAB_MAX_QUERIES);
+    if (k <= 0 || k > CAB_MAX_K) return fail(idx, CAB_ERR_INVALID, "k must be in 1..%d", CAB_MAX_K);
+    if (!std::isfinite(threshold)) return fail(idx, CAB_ERR_INVALID, "threshold must be finite");
+    if (path != CAB_PATH_AUTO && path != CAB_PATH_GEMV && path != CAB_PATH_GEMM) return fail(idx, CAB_ERR_INVALID, "unknown path %d", path);
+    for (int i = 0; i < nq; ++i)
+        if (!(std::isfinite(w_asr[i]) && std::isfinite(w_audio[i]) && w_asr[i] >= 0 && w_audio[i] >= 0))
+            return fail(idx, CAB_ERR_INVALID, "weights must be finite and >= 0");
+    bool use_gemm = false;
+    if (path == CAB_PATH_GEMM) {
+        if (idx->dtype != CAB_BF16) return fail(idx, CAB_ERR_INVALID, "the tensor-core path needs a bf16 index");
+        if (!gemm_path_available()) return fail(idx, CAB_ERR_INVALID, "tensor-core path not built");
+        use_gemm = true;
+    } else if (path == CAB_PATH_AUTO) {
+        use_gemm = idx->dtype == CAB_BF16 && nq >= idx->opt_gemm_min_queries && gemm_path_available();
+    }
+    CU(idx, cudaSetDevice(idx->device));
+    const int n_partials = use_gemm ? gemm_partials_per_query(idx->sm_count)
+                                    : gemv_grid_size(idx->gemv, idx->dtype, idx->sm_count);
+    const int batch = use_gemm ? nq : int(std::min<int64_t>(nq, idx->opt_gemv_batch));
+    int rc = ensure_workspace(idx, nq, k, n_partials, batch, use_gemm ? gemm_workspace_bytes(nq, k, idx->sm_count) : 0);
+    if (rc != CAB_OK) return rc;
+
+    // host staging block: [queries?][w64 asr][w64 audio][w32 a][w32 b]
+    const size_t qbytes = size_t(nq) * CAB_DIM * 4;
+    const size_t in_bytes = (queries_loc == CAB_HOST ? qbytes : 0) + size_t(nq) * (16 + 8);
+    if ((rc = ensure_pinned(idx, &idx->h_in, &idx->h_in_bytes, in_bytes))) return rc;
+    if (idx->ev_in_pending) { CU(idx, cudaEventSynchronize(idx->ev_in)); idx->ev_in_pending = false; }
+    uint8_t *h = idx->h_in;
+    const float *dq = queries;
+    if (queries_loc == CAB_HOST) {
+        memcpy(h, queries, qbytes);
+        CU(idx, cudaMemcpyAsync(idx->d_queries, h, qbytes, cudaMemcpyHostToDevice, s));
+        dq = idx->d_queries;
+        h += qbytes;
+    }
+    double *h64 = reinterpret_cast<double *>(h);
+    float *h32 = reinterpret_cast<float *>(h + size_t(nq) * 16);
+    for (int i = 0; i < nq; ++i) {
+        h64[i] = w_asr[i]; h64[nq + i] = w_audio[i];
+        const double tot = w_asr[i] + w_audio[i];
+        h32[i] = tot > 0 ? float(w_asr[i] / tot) : 0.f;
+        h32[nq + i] = tot > 0 ? float(w_audio[i] / tot) : 0.f;
+    }
+    CU(idx, cudaMemcpyAsync(idx->d_w64, h64, size_t(nq) * 16, cudaMemcpyHostToDevice, s));
+    CU(idx, cudaMemcpyAsync(idx->d_w32, h32, size_t(nq) * 8, cudaMemcpyHostToDevice, s));
+    CU(idx, cudaEventRecord(idx->ev_in, s));
+    idx->ev_in_pending = true;
+
+    idx->timed = false;
+    if (idx->size == 0) {
+        // nothing to scan: every candidate slot is empty
+        CU(idx, cudaMemsetAsync(idx->d_cands, 0xFF, size_t(nq) * k * sizeof(cab_candidate), s));
+        return CAB_OK;
+    }
+
+    ScanArgs sa{};
+    sa.asr = idx->asr; sa.audio = idx->audio; sa.flags = idx->flags; sa.n_rows = idx->size;
+    sa.dtype = idx->dtype; sa.k = k;
+    sa.select_threshold = float(threshold) - 1e-6f;
+    sa.partial_keys = idx->d_partial_keys; sa.partial_count = idx->d_partial_count;
+    sa.n_partials = n_partials; sa.nonfinite = idx->d_nonfinite;
+    FinalizeArgs fa{};
+    fa.asr = idx->asr; fa.audio = idx->audio; fa.flags = idx->flags; fa.dtype = idx->dtype;
+    fa.row_base = idx->row_base; fa.k = k; fa.partial_keys = idx->d_partial_keys;
+    fa.partial_count = idx->d_partial_count; fa.n_partials = n_partials;
+
+    if (idx->opt_time_kernels) CU(idx, cudaEventRecord(idx->ev_t0, s));
+    for (int q0 = 0; q0 < nq; q0 += batch) {
+        const int m = std::min(batch, nq - q0);
+        sa.queries = dq + size_t(q0) * CAB_DIM; sa.wa32 = idx->d_w32 + q0; sa.wb32 = idx->d_w32 + nq + q0;
+        sa.n_queries = m;
+        if (use_gemm) {
+            std::string err;
+            launch_gemm_scan(sa, idx->sm_count, idx->d_gemm_ws, idx->d_gemm_ws_bytes, s, &err);
+            if (!err.empty()) return fail(idx, CAB_ERR_CUDA, "%s", err.c_str());
+        } else {
+            launch_gemv_scan(sa, idx->gemv, idx->sm_count, s);
+        }
+        if (idx->opt_time_kernels && q0 + batch >= nq) CU(idx, cudaEventRecord(idx->ev_t1, s));
+        fa.queries = sa.queries; fa.n_queries = m; fa.cands = idx->d_cands + size_t(q0) * k;
+        launch_finalize(fa, s);
+        idx->launches += 2;
+    }
+    if (idx->opt_time_kernels) idx->timed = true;
+    CU(idx, cudaGetLastError());
+    return CAB_OK;
+}
+
+static int emit_and_return(cab_index *idx, const cab_candidate *cands, int n_lists, int nq, int k,
+                           double threshold, int64_t *out_index, double *out_fusion, float *out_asr,
+                           float *out_audio, uint8_t *out_flags, int32_t *out_count, int out_loc,
+                           cudaStream_t s) {
+    if (out_loc != CAB_HOST && out_loc != CAB_DEVICE) return fail(idx, CAB_ERR_INVALID, "out_loc");
+    if (size_t(n_lists) * k > 1024) return fail(idx, CAB_ERR_INVALID, "n_lists * k must be <= 1024");
+    const OutLayout L = out_layout(nq, k);
+    uint8_t *d = idx->d_out;
+    EmitArgs ea{};
+    ea.cands = cands; ea.n_lists = n_lists; ea.n_queries = nq; ea.k = k;
+    ea.w_asr = idx->d_w64; ea.w_audio = idx->d_w64 + nq; ea.threshold = threshold;
+    const bool dev = out_loc == CAB_DEVICE;
+    ea.out_index = dev && out_index ? out_index : reinterpret_cast<int64_t *>(d + L.index);
+    ea.out_fusion = dev && out_fusion ? out_fusion : reinterpret_cast<double *>(d + L.fusion);
+    ea.out_asr = dev && out_asr ? out_asr : reinterpret_cast<float *>(d + L.asr);
+    ea.out_audio = dev && out_audio ? out_audio : reinterpret_cast<float *>(d + L.audio);
+    ea.out_flags = dev && out_flags ? out_flags : d + L.flags;
+    ea.out_count = dev && out_count ? out_count : reinterpret_cast<int32_t *>(d + L.count);
+    launch_emit(ea, s);
+    idx->launches += 1;
+    CU(idx, cudaGetLastError());
+    if (dev) {
+        if (idx->opt_sync) CU(idx, cudaStreamSynchronize(s));
+        return CAB_OK;
+    }
+    int rc = ensure_pinned(idx, &idx->h_out, &idx->h_out_bytes, L.total);
+    if (rc != CAB_OK) return rc;
+    CU(idx, cudaMemcpyAsync(d + L.nonfinite, idx->d_nonfinite, sizeof(int), cudaMemcpyDeviceToDevice, s));
+    CU(idx, cudaMemcpyAsync(idx->h_out, d, L.total, cudaMemcpyDeviceToHost, s));
+    CU(idx, cudaStreamSynchronize(s));
+    idx->ev_in_pending = false;
+    const uint8_t *h = idx->h_out;
+    if (*reinterpret_cast<const int *>(h + L.nonfinite)) {
+        CU(idx, cudaMemsetAsync(idx->d_nonfinite, 0, sizeof(int), s));
+        CU(idx, cudaStreamSynchronize(s));
+        return fail(idx, CAB_ERR_NONFINITE, "Input contains NaN or infinity (query)");
+    }
+    const size_t n = size_t(nq) * k;
+    if (out_index) memcpy(out_index, h + L.index, n * 8);
+    if (out_fusion) memcpy(out_fusion, h + L.fusion, n * 8);
+    if (out_asr) memcpy(out_asr, h + L.asr, n * 4);
+    if (out_audio) memcpy(out_audio, h + L.audio, n * 4);
+    if (out_flags) memcpy(out_flags, h + L.flags, n);
+    if (out_count) memcpy(out_count, h + L.count, size_t(nq) * 4);
+    return CAB_OK;
+}
+
+int cab_search(cab_index *idx, const float *queries, int queries_loc, const double *w_asr,
+               const double *w_audio, int n_queries, int k, double threshold, int path,
+               int64_t *out_index, double *out_fusion, float *out_asr, float *out_audio,
+               uint8_t *out_flags, int32_t *out_count, int out_loc, void *stream) {
+    CHECK_HANDLE(idx);
+    cudaStream_t s = stream ? (cudaStream_t)stream : idx->own_stream;
+    int rc = run_local(idx, queries, queries_loc, w_asr, w_audio, n_queries, k, threshold, path, s);
+    if (rc != CAB_OK) return rc;
+    return emit_and_return(idx, idx->d_cands, 1, n_queries, k, threshold, out_index, out_fusion,
+                           out_asr, out_audio, out_flags, out_count, out_loc, s);
+}
+
+int cab_search_candidates(cab_index *idx, const float *queries, int queries_loc,
+                          const double *w_asr, const double *w_audio, int n_queries, int k,
+                          double threshold, int path, cab_candidate *out_device, void *stream) {
+    CHECK_HANDLE(idx);
+    if (!out_device) return fail(idx, CAB_ERR_INVALID, "out_device is null");
+    cudaStream_t s = stream ? (cudaStream_t)stream : idx->own_stream;
+    int rc = run_local(idx, queries, queries_loc, w_asr, w_audio, n_queries, k, threshold, path, s);
+    if (rc != CAB_OK) return rc;
+    CU(idx, cudaMemcpyAsync(out_device, idx->d_cands, size_t(n_queries) * k * sizeof(cab_candidate),
+                            cudaMemcpyDeviceToDevice, s));
+    if (idx->opt_sync) CU(idx, cudaStreamSynchronize(s));
+    return CAB_OK;
+}
+
+int cab_merge_candidates(cab_index *idx, const cab_candidate *cands_device, int n_lists,
+                         int n_queries, int k, const double *w_asr, const double *w_audio,
+                         double threshold, int64_t *out_index, double *out_fusion, float *out_asr,
+                         float *out_audio, uint8_t *out_flags, int32_t *out_count, int out_loc,
+                         void *stream) {
+    CHECK_HANDLE(idx);
+    if (!cands_device || !w_asr || !w_audio || n_lists <= 0) return fail(idx, CAB_ERR_INVALID, "bad merge arguments");
+    if (n_queries <= 0 || n_queries > CAB_MAX_QUERIES || k <= 0 || k > CAB_MAX_K) return fail(idx, CAB_ERR_INVALID, "bad n_queries / k");
+    CU(idx, cudaSetDevice(idx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : idx->own_stream;
+    int rc = ensure_workspace(idx, n_queries, k, 1, 1, 0);
+    if (rc != CAB_OK) return rc;
+    if ((rc = ensure_pinned(idx, &idx->h_in, &idx->h_in_bytes, size_t(n_queries) * 16))) return rc;
+    if (idx->ev_in_pending) { CU(idx, cudaEventSynchronize(idx->ev_in)); idx->ev_in_pending = false; }
+    double *h64 = reinterpret_cast<double *>(idx->h_in);
+    for (int i = 0; i < n_queries; ++i) { h64[i] = w_asr[i]; h64[n_queries + i] = w_audio[i]; }
+    CU(idx, cudaMemcpyAsync(idx->d_w64, h64, size_t(n_queries) * 16, cudaMemcpyHostToDevice, s));
+    CU(idx, cudaEventRecord(idx->ev_in, s));
+    idx->ev_in_pending = true;
+    return emit_and_return(idx, cands_device, n_lists, n_queries, k, threshold, out_index, out_fusion,
+                           out_asr, out_audio, out_flags, out_count, out_loc, s);
+}
+
+int cab_index_set_option(cab_index *idx, const char *key, int64_t value) {
+    CHECK_HANDLE(idx);
+    if (!key) return fail(idx, CAB_ERR_INVALID, "null option key");
+    std::string k(key);
+    if (k == "gemv_variant") { if (value < 0 || value > 1) return fail(idx, CAB_ERR_INVALID, "gemv_variant in {0,1}"); idx->gemv.variant = int(value); }
+    else if (k == "gemv_blocks_per_sm") { if (value < 0 || value > 8) return fail(idx, CAB_ERR_INVALID, "gemv_blocks_per_sm in 0..8"); idx->gemv.blocks_per_sm = int(value); }
+    else if (k == "gemv_unroll") { if (value != 0 && value != 1 && value != 2 && value != 4) return fail(idx, CAB_ERR_INVALID, "gemv_unroll in {0,1,2,4}"); idx->gemv.unroll = int(value); }
+    else if (k == "time_kernels") idx->opt_time_kernels = value != 0;
+    else if (k == "sync_after_search") idx->opt_sync = value != 0;
+    else if (k == "gemm_min_queries") { if (value < 1) return fail(idx, CAB_ERR_INVALID, "gemm_min_queries >= 1"); idx->opt_gemm_min_queries = value; }
+    else if (k == "gemv_batch") { if (value < 1 || value > 64) return fail(idx, CAB_ERR_INVALID, "gemv_batch in 1..64"); idx->opt_gemv_batch = value; }
+    else return fail(idx, CAB_ERR_INVALID, "unknown option '%s'", key);
+    return CAB_OK;
+}
+
+int64_t cab_index_get_option(const cab_index *idx, const char *key) {
+    if (!idx || !key) return -1;
+    std::string k(key);
+    if (k == "gemv_variant") return idx->gemv.variant;
+    if (k == "gemv_blocks_per_sm") return idx->gemv.blocks_per_sm;
+    if (k == "gemv_unroll") return idx->gemv.unroll;
+    if (k == "time_kernels") return idx->opt_time_kernels;
+    if (k == "sync_after_search") return idx->opt_sync;
+    if (k == "gemm_min_queries") return idx->opt_gemm_min_queries;
+    if (k == "gemv_batch") return idx->opt_gemv_batch;
+    if (k == "sm_count") return idx->sm_count;
+    if (k == "gemv_grid") return gemv_grid_size(idx->gemv, idx->dtype, idx->sm_count);
+    return -1;
+}
+
+int64_t cab_index_launch_count(const cab_index *idx) { return idx ? idx->launches : -1; }
+
+double cab_index_last_scan_ms(const cab_index *idx) {
+    if (!idx || !idx->timed) return -1.0;
+    if (cudaEventSynchronize(idx->ev_t1) != cudaSuccess) { cudaGetLastError(); return -1.0; }
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, idx->ev_t0, idx->ev_t1) != cudaSuccess) { cudaGetLastError(); return -1.0; }
+    return double(ms);
+}
+

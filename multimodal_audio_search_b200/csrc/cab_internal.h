@@ -1,0 +1,92 @@
+// Host-side internal API between the C-ABI (cab_api.cu) and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/cab.h"
+
+namespace cab {
+
+// ---- ingest (cab_ingest.cu) --------------------------------------------------------------------
+// Normalise n raw fp32 rows (sklearn `normalize` semantics) into the store at row offset `dst_row`.
+// src == nullptr writes zero rows.  *nonfinite (device int) is set to 1 if any value is NaN/Inf.
+void launch_normalize_rows(const float *src, void *dst, int dtype, int64_t dst_row, int64_t n,
+                           int *nonfinite, cudaStream_t s);
+// Deterministic synthetic rows (synth.py) for global rows [r0, r1) of stream 0/1, raw fp32.
+struct SynthParams {
+    uint32_t seed;
+    uint64_t n_total;
+    uint32_t n_plants_total;   // n_queries * plants
+    uint32_t plants;           // per query
+    uint64_t base, inv_stride;
+};
+void launch_synth_rows(const SynthParams &p, int stream_id, int64_t r0, int64_t n, float *out,
+                       cudaStream_t s);
+void launch_synth_flags(uint32_t seed, int partial, int64_t r0, int64_t n, uint8_t *out,
+                        cudaStream_t s);
+void launch_widen_rows(const void *src, int dtype, int64_t r0, int64_t n, float *out,
+                       cudaStream_t s);
+
+// ---- scan (cab_gemv.cu) ------------------------------------------------------------------------
+struct ScanArgs {
+    const void *asr;           // [n_rows x 384] normalised rows, fp32 or bf16
+    const void *audio;
+    const uint8_t *flags;      // [n_rows]
+    int64_t n_rows;
+    int dtype;
+    const float *queries;      // device, raw fp32 [n_queries x 384]
+    const float *wa32;         // device [n_queries] w_asr/(w_asr+w_audio)
+    const float *wb32;
+    int n_queries;
+    int k;
+    float select_threshold;    // fp32 bound used while scanning (slightly below the fp64 one)
+    // outputs: per (query, partial list) sorted keys
+    uint64_t *partial_keys;    // [n_queries][n_partials][k]
+    int32_t *partial_count;    // [n_queries][n_partials]
+    int n_partials;            // == grid size of the scan
+    int *nonfinite;            // set if a query holds NaN/Inf
+};
+struct GemvConfig {
+    int variant;               // 0 = LDG register pipeline, 1 = bulk-copy smem ring
+    int blocks_per_sm;         // 0 = default
+    int unroll;                // 0 = default
+};
+// Number of partial lists (grid size) the GEMV scan will use for this config.
+int gemv_grid_size(const GemvConfig &cfg, int dtype, int sm_count);
+void launch_gemv_scan(const ScanArgs &a, const GemvConfig &cfg, int sm_count, cudaStream_t s);
+
+// ---- finalize + emit (cab_finalize.cu) ----------------------------------------------------------
+struct FinalizeArgs {
+    const void *asr;
+    const void *audio;
+    const uint8_t *flags;
+    int dtype;
+    int64_t row_base;          // global index of local row 0
+    const float *queries;
+    int n_queries;
+    int k;
+    const uint64_t *partial_keys;
+    const int32_t *partial_count;
+    int n_partials;
+    cab_candidate *cands;      // out [n_queries][k], best-first by scan score, index -1 = empty
+};
+void launch_finalize(const FinalizeArgs &a, cudaStream_t s);
+
+struct EmitArgs {
+    const cab_candidate *cands;   // [n_lists][n_queries][k]
+    int n_lists;
+    int n_queries;
+    int k;
+    const double *w_asr;          // device [n_queries]
+    const double *w_audio;
+    double threshold;
+    int64_t *out_index;           // device [n_queries][k] (all required here)
+    double *out_fusion;
+    float *out_asr;
+    float *out_audio;
+    uint8_t *out_flags;
+    int32_t *out_count;
+};
+void launch_emit(const EmitArgs &a, cudaStream_t s);
+
+}  // namespace cab

@@ -1,0 +1,170 @@
+"""Drop-in for the search path of the reference's `DualPipelineAudioSearch`
+(/root/reference/audio_search.py:87-699).
+
+Two ways to use it:
+
+* `accelerate(search_system)` -- patch an existing reference object (the one Streamlit keeps in
+  `st.session_state.search_system`, :708-711): only `search_with_fusion` is replaced; the
+  reference's own `_analyze_query_for_weights`, `text_embedder`, `stats`, `audio_segments`
+  keep being used, so Whisper / MiniLM / the UI stay the reference's code.
+* `DualPipelineAudioSearch` -- a standalone object with the same search-side attributes
+  (`audio_segments`, `text_embedder`, `stats['search_pipeline']`, `search_with_fusion`,
+  `_analyze_query_for_weights`) for callers that do not have the reference installed.
+
+`search_with_fusion(query)` returns what the reference returns: `(results[:10], weight_info)`,
+each result being `{**segment, asr_similarity, audio_similarity, fusion_score,
+effective_asr_weight, effective_audio_weight, query_asr_weight, query_audio_weight}` (:673-682)
+with Python floats; `([], {})` on an empty library before any stats update (:626-627).
+The per-segment loop, threshold, sort and slice (:639-685, :699) run on the GPU (libcab.so).
+"""
+from __future__ import annotations
+
+import time
+import types
+from dataclasses import dataclass
+from typing import Dict, List, Tuple
+
+import numpy as np
+
+from . import query_weights
+from .index import SegmentIndex
+
+TOP_K = 10          # audio_search.py:699
+THRESHOLD = 0.1     # audio_search.py:672
+DIM = 384
+
+
+@dataclass
+class PipelineStats:
+    """Same counters and update rule as the reference's PipelineStats (audio_search.py:23-48)."""
+    pipeline_name: str
+    model_name: str
+    total_calls: int = 0
+    total_processing_time: float = 0.0
+    avg_processing_time: float = 0.0
+    success_rate: float = 1.0
+    successful_extractions: int = 0
+    failed_extractions: int = 0
+
+    def update(self, processing_time: float, success: bool):
+        self.total_calls += 1
+        self.total_processing_time += processing_time
+        self.avg_processing_time = self.total_processing_time / self.total_calls
+        if success:
+            self.successful_extractions += 1
+        else:
+            self.failed_extractions += 1
+        self.success_rate = self.successful_extractions / self.total_calls
+
+
+def _embedding_row(e) -> np.ndarray:
+    a = np.asarray(e, dtype=np.float32).reshape(-1)
+    if a.shape[0] != DIM:
+        raise ValueError(f"Incompatible dimension for X and Y matrices: X.shape[1] == {DIM} "
+                         f"while Y.shape[1] == {a.shape[0]}")
+    return a
+
+
+class _DeviceLibrary:
+    """Keeps a SegmentIndex in step with an append-only `audio_segments` list (:797)."""
+
+    def __init__(self, dtype: str = "fp32", device: int = 0):
+        self.dtype, self.device = dtype, device
+        self.index: SegmentIndex | None = None
+        self.n_synced = 0
+        self._last_seg = None
+
+    def sync(self, segments: List[Dict]) -> SegmentIndex:
+        if self.index is None:
+            self.index = SegmentIndex(self.dtype, capacity=max(1024, len(segments)), device=self.device)
+        # the reference only ever appends; if the list was replaced or shrunk, rebuild
+        if self.n_synced > len(segments) or (self.n_synced and segments[self.n_synced - 1] is not self._last_seg):
+            self.index.clear()
+            self.n_synced = 0
+        n_new = len(segments) - self.n_synced
+        if n_new > 0:
+            new = segments[self.n_synced:]
+            asr = np.zeros((n_new, DIM), dtype=np.float32)
+            audio = np.zeros((n_new, DIM), dtype=np.float32)
+            flags = np.zeros(n_new, dtype=np.uint8)
+            for i, seg in enumerate(new):
+                if seg["asr_embedding"] is not None:                  # :644
+                    asr[i] = _embedding_row(seg["asr_embedding"])
+                if seg["audio_embedding"] is not None:                # :649
+                    audio[i] = _embedding_row(seg["audio_embedding"])
+                flags[i] = (1 if seg["asr_success"] else 0) | (2 if seg["audio_success"] else 0)
+            self.index.append(asr, audio, flags)                      # ValueError on NaN/Inf
+            self.n_synced = len(segments)
+            self._last_seg = segments[-1]
+        return self.index
+
+
+def _b200_search_with_fusion(self, query: str) -> Tuple[List[Dict], Dict]:
+    """GPU-backed body of search_with_fusion; `self` is a reference-compatible engine."""
+    if not self.audio_segments:                                       # :626-627
+        return [], {}
+    start_time = time.time()
+    asr_weight, audio_weight, weight_analysis = self._analyze_query_for_weights(query)   # :632
+    query_embedding = _embedding_row(self.text_embedder.encode(query))                   # :635
+    index = self._cab_library.sync(self.audio_segments)
+    res = index.search(query_embedding[None, :], asr_weight, audio_weight, k=TOP_K, threshold=THRESHOLD)
+
+    results = []
+    for j in range(int(res.count[0])):
+        segment = self.audio_segments[int(res.indices[0, j])]
+        asr_similarity = float(res.asr_sim[0, j])                     # :646
+        audio_similarity = float(res.audio_sim[0, j])                 # :651
+        effective_asr_weight = asr_weight if segment["asr_success"] else 0       # :656-657
+        effective_audio_weight = audio_weight if segment["audio_success"] else 0
+        total_weight = effective_asr_weight + effective_audio_weight
+        effective_asr_weight /= total_weight                          # :663-664
+        effective_audio_weight /= total_weight
+        fusion_score = (effective_asr_weight * asr_similarity +
+                        effective_audio_weight * audio_similarity)    # :667-670
+        results.append({
+            **segment,
+            "asr_similarity": asr_similarity,
+            "audio_similarity": audio_similarity,
+            "fusion_score": fusion_score,
+            "effective_asr_weight": effective_asr_weight,
+            "effective_audio_weight": effective_audio_weight,
+            "query_asr_weight": asr_weight,
+            "query_audio_weight": audio_weight,
+        })
+    processing_time = time.time() - start_time
+    self.stats["search_pipeline"].update(processing_time, success=len(results) > 0)      # :688-689
+    weight_info = {"asr_weight": asr_weight, "audio_weight": audio_weight,
+                   "analysis": weight_analysis, "query": query}       # :692-697
+    return results, weight_info
+
+
+def accelerate(search_system, dtype: str = "fp32", device: int = 0):
+    """Replace `search_system.search_with_fusion` (a reference DualPipelineAudioSearch, or any
+    object with the same attributes) by the B200 path.  Returns the same object."""
+    search_system._cab_library = _DeviceLibrary(dtype, device)
+    search_system.search_with_fusion = types.MethodType(_b200_search_with_fusion, search_system)
+    return search_system
+
+
+class DualPipelineAudioSearch:
+    """Search-side mirror of the reference class (:87-140, :457-699).  Model loading and audio
+    ingest are the reference's business: populate `audio_segments` with its segment records
+    (:275-294) and set `text_embedder` to anything with `.encode(str) -> float32[384]`."""
+
+    def __init__(self, dtype: str = "fp32", device: int = 0, text_embedder=None):
+        self.text_embedder = text_embedder
+        self.stats = {"search_pipeline": PipelineStats("Search Pipeline", "Cosine Similarity")}   # :107
+        self.audio_segments: List[Dict] = []                                                      # :115
+        self._cab_library = _DeviceLibrary(dtype, device)
+
+    def _analyze_query_for_weights(self, query: str):
+        return query_weights.analyze_query_for_weights(query)
+
+    search_with_fusion = _b200_search_with_fusion
+
+    # -- beyond the reference: many queries per call (BASELINE configs 3-5) ----------------------
+    def search_batch(self, query_vectors, asr_weights, audio_weights, k: int = TOP_K,
+                     threshold: float = THRESHOLD, path: str = "auto"):
+        """Top-k for a batch of already-embedded queries; returns a SearchResult."""
+        index = self._cab_library.sync(self.audio_segments)
+        return index.search(query_vectors, asr_weights, audio_weights, k=k, threshold=threshold, path=path)

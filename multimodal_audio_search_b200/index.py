@@ -1,0 +1,253 @@
+"""`SegmentIndex`: the device-resident dual-corpus segment store + fused search, over the C-ABI.
+
+Host numpy arrays go through the library's pinned staging (copies inside the call); CUDA torch
+tensors are passed by pointer on torch's current stream and results come back as CUDA tensors.
+PyTorch is used only as the owner of device memory / streams -- all arithmetic is in libcab.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _native as N
+
+_DTYPES = {"fp32": N.CAB_F32, "f32": N.CAB_F32, "float32": N.CAB_F32,
+           "bf16": N.CAB_BF16, "bfloat16": N.CAB_BF16}
+_PATHS = {"auto": N.CAB_PATH_AUTO, "gemv": N.CAB_PATH_GEMV, "gemm": N.CAB_PATH_GEMM}
+
+
+@dataclass
+class SearchResult:
+    """Per query: `count[q]` results, best first; slots beyond count hold index -1."""
+    indices: "np.ndarray"      # int64  [Q, k] global segment index
+    fusion: "np.ndarray"       # float64 [Q, k]
+    asr_sim: "np.ndarray"      # float32 [Q, k]
+    audio_sim: "np.ndarray"    # float32 [Q, k]
+    flags: "np.ndarray"        # uint8   [Q, k]
+    count: "np.ndarray"        # int32   [Q]
+
+
+def _is_torch_cuda(x) -> bool:
+    return hasattr(x, "is_cuda") and bool(x.is_cuda)
+
+
+def _np_f32(x, cols=None):
+    a = np.ascontiguousarray(x, dtype=np.float32)
+    if cols is not None and (a.ndim != 2 or a.shape[1] != cols):
+        raise ValueError(f"expected a [n x {cols}] float32 matrix, got shape {a.shape}")
+    return a
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class SegmentIndex:
+    def __init__(self, dtype: str = "fp32", capacity: int = 0, device: int = 0, dim: int = N.CAB_DIM):
+        if dtype not in _DTYPES:
+            raise ValueError(f"dtype must be one of {sorted(_DTYPES)}")
+        self._lib = N.lib()
+        self._h = C.c_void_p()
+        N.check(self._lib.cab_index_create(dim, _DTYPES[dtype], int(capacity), int(device), C.byref(self._h)))
+        self.dtype = "bf16" if _DTYPES[dtype] == N.CAB_BF16 else "fp32"
+        self.device = int(device)
+        self.dim = dim
+
+    # -- lifetime ------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.cab_index_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self) -> int:
+        return int(self._lib.cab_index_size(self._h))
+
+    @property
+    def capacity(self) -> int:
+        return int(self._lib.cab_index_capacity(self._h))
+
+    @property
+    def row_base(self) -> int:
+        return int(self._lib.cab_index_row_base(self._h))
+
+    @row_base.setter
+    def row_base(self, v: int):
+        N.check(self._lib.cab_index_set_row_base(self._h, int(v)), self._h)
+
+    def reserve(self, rows: int):
+        N.check(self._lib.cab_index_reserve(self._h, int(rows)), self._h)
+
+    def clear(self):
+        N.check(self._lib.cab_index_clear(self._h), self._h)
+
+    def set_option(self, key: str, value: int):
+        N.check(self._lib.cab_index_set_option(self._h, key.encode(), int(value)), self._h)
+
+    def get_option(self, key: str) -> int:
+        return int(self._lib.cab_index_get_option(self._h, key.encode()))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.cab_index_launch_count(self._h))
+
+    def last_scan_ms(self) -> float:
+        return float(self._lib.cab_index_last_scan_ms(self._h))
+
+    def _stream(self):
+        import torch
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # -- ingest --------------------------------------------------------------------------------
+    def append(self, asr_rows, audio_rows, flags=None):
+        """Append segments.  Rows: [n x 384] float32 (numpy, or CUDA torch tensors), raw; `None`
+        for a whole corpus means "no embedding" for every row.  flags: uint8 [n] (bit0 asr_success,
+        bit1 audio_success) or None (= 3)."""
+        if _is_torch_cuda(asr_rows) or _is_torch_cuda(audio_rows):
+            import torch
+            ts = [t for t in (asr_rows, audio_rows) if t is not None]
+            n = ts[0].shape[0]
+            for t in ts:
+                if t.dtype != torch.float32 or t.dim() != 2 or t.shape[1] != self.dim or not t.is_contiguous():
+                    raise ValueError("device rows must be contiguous float32 [n x 384]")
+            f = None
+            if flags is not None:
+                f = flags if _is_torch_cuda(flags) else torch.as_tensor(np.asarray(flags, np.uint8)).cuda(self.device)
+                if f.dtype != torch.uint8 or f.numel() != n:
+                    raise ValueError("flags must be uint8 [n]")
+            N.check(self._lib.cab_index_append(
+                self._h, None if asr_rows is None else C.c_void_p(asr_rows.data_ptr()),
+                None if audio_rows is None else C.c_void_p(audio_rows.data_ptr()),
+                None if f is None else C.c_void_p(f.data_ptr()), n, N.CAB_DEVICE, self._stream()), self._h)
+            return
+        a = None if asr_rows is None else _np_f32(asr_rows, self.dim)
+        b = None if audio_rows is None else _np_f32(audio_rows, self.dim)
+        if a is None and b is None:
+            raise ValueError("at least one corpus must be given")
+        n = (a if a is not None else b).shape[0]
+        if a is not None and b is not None and a.shape[0] != b.shape[0]:
+            raise ValueError("asr_rows and audio_rows differ in length")
+        f = None
+        if flags is not None:
+            f = np.ascontiguousarray(flags, dtype=np.uint8)
+            if f.shape != (n,):
+                raise ValueError("flags must be uint8 [n]")
+        N.check(self._lib.cab_index_append(self._h, _ptr(a), _ptr(b), _ptr(f), n, N.CAB_HOST, None), self._h)
+
+    def append_synth(self, seed: int, n_total: int, r0: int = 0, r1: int | None = None,
+                     n_queries: int = 1, plants: int = 0, partial: bool = False):
+        """Generate global rows [r0, r1) of the synthetic library on the device (synth.py twin)."""
+        r1 = n_total if r1 is None else r1
+        N.check(self._lib.cab_index_append_synth(self._h, seed & 0xFFFFFFFF, n_total, r0, r1,
+                                                 n_queries, plants, int(bool(partial)), None), self._h)
+
+    def read_rows(self, corpus: int, r0: int, r1: int) -> np.ndarray:
+        out = np.empty((r1 - r0, self.dim), dtype=np.float32)
+        N.check(self._lib.cab_index_read_rows(self._h, corpus, r0, r1, _ptr(out), N.CAB_HOST), self._h)
+        return out
+
+    # -- search --------------------------------------------------------------------------------
+    @staticmethod
+    def _weights(w_asr, w_audio, nq):
+        wa = np.ascontiguousarray(np.broadcast_to(np.asarray(w_asr, dtype=np.float64), (nq,)))
+        wb = np.ascontiguousarray(np.broadcast_to(np.asarray(w_audio, dtype=np.float64), (nq,)))
+        return wa, wb
+
+    def search(self, queries, w_asr=0.5, w_audio=0.5, k: int = 10, threshold: float = 0.1,
+               path: str = "auto") -> SearchResult:
+        """Fused dual-corpus top-k.  numpy queries -> numpy results (host staging + copies inside
+        the call); CUDA torch queries -> CUDA torch results on torch's current stream."""
+        if _is_torch_cuda(queries):
+            return self._search_device(queries, w_asr, w_audio, k, threshold, path)
+        q = _np_f32(np.atleast_2d(queries), self.dim)
+        nq = q.shape[0]
+        wa, wb = self._weights(w_asr, w_audio, nq)
+        out = SearchResult(np.empty((nq, k), np.int64), np.empty((nq, k), np.float64),
+                           np.empty((nq, k), np.float32), np.empty((nq, k), np.float32),
+                           np.empty((nq, k), np.uint8), np.empty((nq,), np.int32))
+        N.check(self._lib.cab_search(self._h, _ptr(q), N.CAB_HOST, _ptr(wa), _ptr(wb), nq, k,
+                                     float(threshold), _PATHS[path], _ptr(out.indices), _ptr(out.fusion),
+                                     _ptr(out.asr_sim), _ptr(out.audio_sim), _ptr(out.flags),
+                                     _ptr(out.count), N.CAB_HOST, None), self._h)
+        return out
+
+    def _search_device(self, queries, w_asr, w_audio, k, threshold, path) -> SearchResult:
+        import torch
+        q = queries if queries.dim() == 2 else queries.unsqueeze(0)
+        if q.dtype != torch.float32 or q.shape[1] != self.dim or not q.is_contiguous():
+            raise ValueError("device queries must be contiguous float32 [Q x 384]")
+        nq = q.shape[0]
+        wa, wb = self._weights(w_asr, w_audio, nq)
+        dev = q.device
+        out = SearchResult(torch.empty((nq, k), dtype=torch.int64, device=dev),
+                           torch.empty((nq, k), dtype=torch.float64, device=dev),
+                           torch.empty((nq, k), dtype=torch.float32, device=dev),
+                           torch.empty((nq, k), dtype=torch.float32, device=dev),
+                           torch.empty((nq, k), dtype=torch.uint8, device=dev),
+                           torch.empty((nq,), dtype=torch.int32, device=dev))
+        p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+        N.check(self._lib.cab_search(self._h, p(q), N.CAB_DEVICE, _ptr(wa), _ptr(wb), nq, k,
+                                     float(threshold), _PATHS[path], p(out.indices), p(out.fusion),
+                                     p(out.asr_sim), p(out.audio_sim), p(out.flags), p(out.count),
+                                     N.CAB_DEVICE, self._stream()), self._h)
+        return out
+
+    # -- sharded search (corpus split by segment over ranks) -----------------------------------
+    def search_candidates(self, queries, w_asr=0.5, w_audio=0.5, k: int = 10,
+                          threshold: float = 0.1, path: str = "auto"):
+        """Local top-k of this shard as packed cab_candidate records: CUDA uint8 [Q, k, 24]."""
+        import torch
+        if _is_torch_cuda(queries):
+            q = queries if queries.dim() == 2 else queries.unsqueeze(0)
+            qp, loc, nq = C.c_void_p(q.data_ptr()), N.CAB_DEVICE, q.shape[0]
+        else:
+            q = _np_f32(np.atleast_2d(queries), self.dim)
+            qp, loc, nq = _ptr(q), N.CAB_HOST, q.shape[0]
+        wa, wb = self._weights(w_asr, w_audio, nq)
+        out = torch.empty((nq, k, N.CANDIDATE_BYTES), dtype=torch.uint8, device=f"cuda:{self.device}")
+        N.check(self._lib.cab_search_candidates(self._h, qp, loc, _ptr(wa), _ptr(wb), nq, k,
+                                                float(threshold), _PATHS[path],
+                                                C.c_void_p(out.data_ptr()), self._stream()), self._h)
+        return out
+
+    def merge_candidates(self, gathered, w_asr=0.5, w_audio=0.5, k: int = 10,
+                         threshold: float = 0.1, to_host: bool = True) -> SearchResult:
+        """Merge candidate blocks of all shards: CUDA uint8 [world, Q, k, 24] -> final top-k."""
+        import torch
+        world, nq = gathered.shape[0], gathered.shape[1]
+        if gathered.shape[2] != k or gathered.shape[3] != N.CANDIDATE_BYTES or not gathered.is_contiguous():
+            raise ValueError("gathered must be contiguous uint8 [world, Q, k, 24]")
+        wa, wb = self._weights(w_asr, w_audio, nq)
+        if to_host:
+            out = SearchResult(np.empty((nq, k), np.int64), np.empty((nq, k), np.float64),
+                               np.empty((nq, k), np.float32), np.empty((nq, k), np.float32),
+                               np.empty((nq, k), np.uint8), np.empty((nq,), np.int32))
+            p, loc = _ptr, N.CAB_HOST
+        else:
+            dev = gathered.device
+            out = SearchResult(torch.empty((nq, k), dtype=torch.int64, device=dev),
+                               torch.empty((nq, k), dtype=torch.float64, device=dev),
+                               torch.empty((nq, k), dtype=torch.float32, device=dev),
+                               torch.empty((nq, k), dtype=torch.float32, device=dev),
+                               torch.empty((nq, k), dtype=torch.uint8, device=dev),
+                               torch.empty((nq,), dtype=torch.int32, device=dev))
+            p, loc = (lambda t: C.c_void_p(t.data_ptr())), N.CAB_DEVICE
+        N.check(self._lib.cab_merge_candidates(self._h, C.c_void_p(gathered.data_ptr()), world, nq, k,
+                                               _ptr(wa), _ptr(wb), float(threshold), p(out.indices),
+                                               p(out.fusion), p(out.asr_sim), p(out.audio_sim),
+                                               p(out.flags), p(out.count), loc, self._stream()), self._h)
+        return out
+
+
+def synth_queries(seed: int, q0: int, q1: int, device: int = 0) -> np.ndarray:
+    """Raw synthetic query vectors generated by the device twin of synth.raw_queries."""
+    out = np.empty((q1 - q0, N.CAB_DIM), dtype=np.float32)
+    N.check(N.lib().cab_synth_queries(device, seed & 0xFFFFFFFF, q0, q1, _ptr(out), N.CAB_HOST))
+    return out

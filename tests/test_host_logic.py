@@ -1,0 +1,50 @@
+"""CPU-only host logic: the product's query-weight rule against the reference-minted goldens,
+and the synthetic generator's structural guarantees."""
+import numpy as np
+
+from multimodal_audio_search_b200 import query_weights, synth
+
+
+def test_query_weights_match_reference(query_weight_cases):
+    for rec in query_weight_cases:
+        got = query_weights.analyze_query_for_weights(rec["query"])
+        assert got == (rec["asr_weight"], rec["audio_weight"], rec["analysis"]), rec["query"]
+
+
+def test_weight_range_and_sum():
+    for a in range(0, 9):
+        for b in range(0, 9):
+            wa, wb, _ = query_weights.weights_from_matches(a, b)
+            assert 0.2 - 1e-12 <= wa <= 0.8 + 1e-12 and abs(wa + wb - 1.0) < 1e-12
+    assert query_weights.weights_from_matches(0, 2)[0] == 0.30000000000000004
+
+
+def test_synth_shards_are_the_same_library():
+    seed, n = 9, 1000
+    a, b, f, spec = synth.library(seed, n, n_queries=3, plants=7, partial=True)
+    parts = [synth.library(seed, n, 3, 7, True, r0=r0, r1=r1) for r0, r1 in ((0, 333), (333, 900), (900, 1000))]
+    np.testing.assert_array_equal(np.concatenate([p[0] for p in parts]), a)
+    np.testing.assert_array_equal(np.concatenate([p[1] for p in parts]), b)
+    np.testing.assert_array_equal(np.concatenate([p[2] for p in parts]), f)
+    assert a.dtype == np.float32 and np.all(a == np.round(a))            # integer valued
+    rows = np.concatenate([synth.plant_rows_of_query(spec, q) for q in range(3)])
+    assert len(set(rows.tolist())) == 21                                   # collision free
+    g = synth.plant_of_rows(spec, np.arange(n))
+    assert sorted(g[g >= 0].tolist()) == list(range(21))
+
+
+def test_synth_plants_are_near_their_query():
+    seed, n = 4, 5000
+    a, b, _, spec = synth.library(seed, n, n_queries=2, plants=30)
+    q = synth.raw_queries(seed, 0, 2)
+    for qi in range(2):
+        rows = synth.plant_rows_of_query(spec, qi)
+        qa = q[qi] / np.linalg.norm(q[qi])
+        planted = []
+        for t, r in enumerate(rows):
+            kind = (qi * 30 + t) % 3
+            ca = a[r] @ qa / np.linalg.norm(a[r])
+            cb = b[r] @ qa / np.linalg.norm(b[r])
+            planted += [ca] if kind == 0 else [cb] if kind == 1 else [ca, cb]
+        # cosine ~= m/sqrt(m^2+n^2) with m, n in 1..8: spread over (0.12, 0.99)
+        assert min(planted) > -0.05 and max(planted) > 0.9 and np.mean(planted) > 0.5
