@@ -110,11 +110,12 @@ def cpu_baseline(n_rows, dtype, k, max_seconds=25.0):
     b /= np.linalg.norm(b, axis=1, keepdims=True)
     f = np.full(sample, 3, np.uint8)
     q = rng.standard_normal(384).astype(np.float32)
-    no.search(q, a, b, f, 0.5, 0.5, k=k)
+    q /= np.linalg.norm(q)
+    no.search_prenormalized(q, a, b, f, 0.5, 0.5, k=k)
     times, t_end = [], time.perf_counter() + max_seconds
     while len(times) < 7 and time.perf_counter() < t_end:
         t0 = time.perf_counter()
-        no.search(q, a, b, f, 0.5, 0.5, k=k)
+        no.search_prenormalized(q, a, b, f, 0.5, 0.5, k=k)
         times.append(time.perf_counter() - t0)
     best = min(times)
     try:
@@ -124,8 +125,9 @@ def cpu_baseline(n_rows, dtype, k, max_seconds=25.0):
         threads = os.cpu_count()
     return {"value": (sample / n_rows) / best, "unit": "queries/s", "cores": int(threads),
             "host_cpus": os.cpu_count(), "kind": "port",
-            "sample": f"oracle/numpy_oracle.search on {sample} of {n_rows} segments (isotropic unit rows), "
-                      f"best of {len(times)}; scaled by segments to the full workload", "dtype": "fp32"}
+            "sample": f"oracle/numpy_oracle.search_prenormalized (rows normalised once, 2 sgemv + fp64 fusion + "
+                      f"top-k per query) on {sample} of {n_rows} segments, isotropic unit rows, best of "
+                      f"{len(times)}; scaled by segments to the full workload", "dtype": "fp32"}
 
 
 def run_reference(args):
@@ -144,11 +146,12 @@ def run_reference(args):
     b /= np.linalg.norm(b, axis=1, keepdims=True)
     f = np.full(sample, 3, np.uint8)
     qs = rng.standard_normal((args.steps + args.warmup, 384)).astype(np.float32)
+    qs /= np.linalg.norm(qs, axis=1, keepdims=True)
     for i in range(args.warmup):
-        no.search(qs[i], a, b, f, 0.5, 0.5, k=k)
+        no.search_prenormalized(qs[i], a, b, f, 0.5, 0.5, k=k)
     t0 = time.perf_counter()
     for i in range(args.steps):
-        no.search(qs[args.warmup + i], a, b, f, 0.5, 0.5, k=k)
+        no.search_prenormalized(qs[args.warmup + i], a, b, f, 0.5, 0.5, k=k)
     dt = time.perf_counter() - t0
     scale = sample / n_rows
     val = args.steps * nq * scale / dt * (n_rows / 1e6)
@@ -158,8 +161,9 @@ def run_reference(args):
     except Exception:
         threads = os.cpu_count()
     cb = {"value": val, "unit": "queries/s (per 1M segments)", "cores": int(threads), "kind": "port",
-          "sample": f"each step = 1 query over {sample} of {n_rows} segments through oracle/numpy_oracle.search "
-                    f"(vectorised restatement of audio_search.py:639-699)"}
+          "sample": f"each step = 1 query over {sample} of {n_rows} segments through "
+                    f"oracle/numpy_oracle.search_prenormalized (vectorised restatement of audio_search.py:639-699 "
+                    f"with rows normalised once at ingest; the literal reference loop runs at ~0.84 ms/segment)"}
     print(json.dumps({
         "impl": "reference", "metric": "fused dual-corpus 384D top-k queries/s", "value": val,
         "unit": "queries/s (per 1M segments)", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,

@@ -146,8 +146,9 @@ CAB_API int cab_merge_candidates(cab_index *idx, const cab_candidate *cands_devi
                          void *stream);
 
 /* ---- tuning / introspection -------------------------------------------------------------- */
-/* Options: "gemv_variant" (0 = LDG register pipeline, 1 = TMA bulk smem ring),
- * "gemv_blocks_per_sm", "gemv_unroll", "sync_after_search" ... ; unknown keys fail. */
+/* Options: "gemv_unroll" (row-steps in flight per warp: 1/2/4/8, 0 = default),
+ * "gemv_blocks_per_sm" (resident CTAs per SM, 0 = default), "gemv_batch", "gemm_min_queries",
+ * "time_kernels", "sync_after_search"; unknown keys fail. */
 CAB_API int cab_index_set_option(cab_index *idx, const char *key, int64_t value);
 CAB_API int64_t cab_index_get_option(const cab_index *idx, const char *key);
 /* Kernels launched by this handle since creation (for bench.py's gpu_launches). */

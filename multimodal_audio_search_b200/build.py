@@ -19,7 +19,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libcab.so")
 
-SOURCES = ["cab_api.cu", "cab_ingest.cu", "cab_gemv.cu", "cab_gemv_bulk.cu", "cab_finalize.cu",
+SOURCES = ["cab_api.cu", "cab_ingest.cu", "cab_gemv.cu", "cab_finalize.cu",
            "cab_gemm_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xptxas", "-v",

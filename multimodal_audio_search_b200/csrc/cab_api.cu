@@ -36,11 +36,11 @@ struct cab_index {
     uint8_t *flags = nullptr;
     cudaStream_t own_stream = nullptr;
     // search workspace (device)
-    float *d_queries = nullptr;    size_t sz_queries = 0;   // [n_queries x 384]
-    double *d_w64 = nullptr;       size_t sz_w64 = 0;       // [2 x n_queries]
-    float *d_w32 = nullptr;        size_t sz_w32 = 0;       // [2 x n_queries]
+    // per-search parameter block, one H2D copy: [w64 asr|w64 audio|w32 a|w32 b|queries (if host)]
+    uint8_t *d_params = nullptr;   size_t sz_params = 0;
+    double *d_w64 = nullptr;       // views into d_params, set by stage_params
+    float *d_w32 = nullptr;
     uint64_t *d_partial_keys = nullptr;  size_t sz_pkeys = 0;
-    int32_t *d_partial_count = nullptr;  size_t sz_pcount = 0;
     cab_candidate *d_cands = nullptr;    size_t sz_cands = 0;
     uint8_t *d_out = nullptr;      size_t d_out_bytes = 0;  // packed outputs
     uint8_t *d_gemm_ws = nullptr;  size_t d_gemm_ws_bytes = 0;
@@ -177,8 +177,8 @@ int cab_index_destroy(cab_index *idx) {
     cudaSetDevice(idx->device);
     if (idx->own_stream) cudaStreamSynchronize(idx->own_stream);
     cudaFree(idx->asr); cudaFree(idx->audio); cudaFree(idx->flags);
-    cudaFree(idx->d_queries); cudaFree(idx->d_w64); cudaFree(idx->d_w32);
-    cudaFree(idx->d_partial_keys); cudaFree(idx->d_partial_count); cudaFree(idx->d_cands);
+    cudaFree(idx->d_params);
+    cudaFree(idx->d_partial_keys); cudaFree(idx->d_cands);
     cudaFree(idx->d_out); cudaFree(idx->d_gemm_ws); cudaFree(idx->d_nonfinite); cudaFree(idx->d_rows);
     cudaFreeHost(idx->h_in); cudaFreeHost(idx->h_out); cudaFreeHost(idx->h_rows);
     if (idx->ev_in) cudaEventDestroy(idx->ev_in);
@@ -333,7 +333,7 @@ int cab_index_append_synth(cab_index *idx, uint32_t seed, int64_t n_total, int64
         void *dst = st == 0 ? idx->asr : idx->audio;
         for (int64_t r = 0; r < n_rows; r += chunk) {
             const int64_t m = std::min(chunk, n_rows - r);
-            launch_synth_rows(p, st, r0 + r, m, idx->d_rows, s);
+            launch_synth_rows(p, st, partial ? 1 : 0, r0 + r, m, idx->d_rows, s);
             launch_normalize_rows(idx->d_rows, dst, idx->dtype, idx->size + r, m, idx->d_nonfinite, s);
             idx->launches += 2;
         }
@@ -356,7 +356,7 @@ int cab_synth_queries(int device, uint32_t seed, int q0, int q1, float *out, int
     const size_t bytes = size_t(q1 - q0) * CAB_DIM * sizeof(float);
     float *d = out;
     if (out_loc == CAB_HOST) CU(nullptr, cudaMalloc((void **)&d, bytes));
-    launch_synth_rows(p, 2, q0, q1 - q0, d, 0);
+    launch_synth_rows(p, 2, 0, q0, q1 - q0, d, 0);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess && out_loc == CAB_HOST) e = cudaMemcpy(out, d, bytes, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -414,26 +414,76 @@ static int ensure_dev(cab_index *idx, T **p, size_t *have, size_t want) {
 
 static int ensure_workspace(cab_index *idx, int nq, int k, int n_partials, int scan_batch, size_t gemm_ws) {
     int rc;
-    if ((rc = ensure_dev(idx, &idx->d_queries, &idx->sz_queries, size_t(nq) * CAB_DIM * 4))) return rc;
-    if ((rc = ensure_dev(idx, &idx->d_w64, &idx->sz_w64, size_t(nq) * 2 * 8))) return rc;
-    if ((rc = ensure_dev(idx, &idx->d_w32, &idx->sz_w32, size_t(nq) * 2 * 4))) return rc;
+    if ((rc = ensure_dev(idx, &idx->d_params, &idx->sz_params, size_t(nq) * (24 + CAB_DIM * 4)))) return rc;
     if ((rc = ensure_dev(idx, &idx->d_partial_keys, &idx->sz_pkeys, size_t(scan_batch) * n_partials * k * 8))) return rc;
-    if ((rc = ensure_dev(idx, &idx->d_partial_count, &idx->sz_pcount, size_t(scan_batch) * n_partials * 4))) return rc;
     if ((rc = ensure_dev(idx, &idx->d_cands, &idx->sz_cands, size_t(nq) * k * sizeof(cab_candidate)))) return rc;
     if ((rc = ensure_dev(idx, &idx->d_out, &idx->d_out_bytes, out_layout(nq, k).total))) return rc;
     if (gemm_ws && (rc = ensure_dev(idx, &idx->d_gemm_ws, &idx->d_gemm_ws_bytes, gemm_ws))) return rc;
     return CAB_OK;
 }
 
-// Stage queries + weights on the device; run scan + finalize -> idx->d_cands[nq x k].
+// Resolve output pointers for the emit stage (user device pointers, or the packed internal block).
+static EmitArgs make_emit(cab_index *idx, int n_lists, int nq, int k, double threshold,
+                          int64_t *out_index, double *out_fusion, float *out_asr, float *out_audio,
+                          uint8_t *out_flags, int32_t *out_count, int out_loc) {
+    const OutLayout L = out_layout(nq, k);
+    uint8_t *d = idx->d_out;
+    EmitArgs ea{};
+    ea.n_lists = n_lists; ea.n_queries = nq; ea.k = k;
+    ea.w_asr = idx->d_w64; ea.w_audio = idx->d_w64 + nq; ea.threshold = threshold;
+    const bool dev = out_loc == CAB_DEVICE;
+    ea.out_index = dev && out_index ? out_index : reinterpret_cast<int64_t *>(d + L.index);
+    ea.out_fusion = dev && out_fusion ? out_fusion : reinterpret_cast<double *>(d + L.fusion);
+    ea.out_asr = dev && out_asr ? out_asr : reinterpret_cast<float *>(d + L.asr);
+    ea.out_audio = dev && out_audio ? out_audio : reinterpret_cast<float *>(d + L.audio);
+    ea.out_flags = dev && out_flags ? out_flags : d + L.flags;
+    ea.out_count = dev && out_count ? out_count : reinterpret_cast<int32_t *>(d + L.count);
+    ea.nonfinite = idx->d_nonfinite;
+    ea.nonfinite_out = reinterpret_cast<int *>(d + L.nonfinite);
+    return ea;
+}
+
+// One H2D copy of the per-search parameter block (weights, and the queries if they are on the host).
+static int stage_params(cab_index *idx, const float *queries, int queries_loc, const double *w_asr,
+                        const double *w_audio, int nq, cudaStream_t s, const float **dq) {
+    const size_t wbytes = size_t(nq) * 24;
+    const size_t qbytes = queries && queries_loc == CAB_HOST ? size_t(nq) * CAB_DIM * 4 : 0;
+    int rc = ensure_pinned(idx, &idx->h_in, &idx->h_in_bytes, wbytes + qbytes);
+    if (rc != CAB_OK) return rc;
+    if (idx->ev_in_pending) { CU(idx, cudaEventSynchronize(idx->ev_in)); idx->ev_in_pending = false; }
+    double *h64 = reinterpret_cast<double *>(idx->h_in);
+    float *h32 = reinterpret_cast<float *>(idx->h_in + size_t(nq) * 16);
+    for (int i = 0; i < nq; ++i) {
+        h64[i] = w_asr[i]; h64[nq + i] = w_audio[i];
+        const double tot = w_asr[i] + w_audio[i];
+        h32[i] = tot > 0 ? float(w_asr[i] / tot) : 0.f;
+        h32[nq + i] = tot > 0 ? float(w_audio[i] / tot) : 0.f;
+    }
+    if (qbytes) memcpy(idx->h_in + wbytes, queries, qbytes);
+    CU(idx, cudaMemcpyAsync(idx->d_params, idx->h_in, wbytes + qbytes, cudaMemcpyHostToDevice, s));
+    CU(idx, cudaEventRecord(idx->ev_in, s));
+    idx->ev_in_pending = true;
+    idx->d_w64 = reinterpret_cast<double *>(idx->d_params);
+    idx->d_w32 = reinterpret_cast<float *>(idx->d_params + size_t(nq) * 16);
+    if (dq) *dq = qbytes ? reinterpret_cast<const float *>(idx->d_params + wbytes) : queries;
+    return CAB_OK;
+}
+
+// Stage parameters; run scan + finalize -> idx->d_cands[nq x k]; with `out` != null (single GPU)
+// the finalize kernel also emits the final results.
+struct UserOut {
+    int64_t *index; double *fusion; float *asr; float *audio; uint8_t *flags; int32_t *count; int loc;
+};
 static int run_local(cab_index *idx, const float *queries, int queries_loc, const double *w_asr,
                      const double *w_audio, int nq, int k, double threshold, int path,
-                     cudaStream_t s) {
+                     const UserOut *out, cudaStream_t s) {
     if (!queries || !w_asr || !w_audio) return fail(idx, CAB_ERR_INVALID, "queries / weights are null");
+    if (queries_loc != CAB_HOST && queries_loc != CAB_DEVICE) return fail(idx, CAB_ERR_INVALID, "queries_loc");
     if (nq <= 0 || nq > CAB_MAX_QUERIES) return fail(idx, CAB_ERR_INVALID, "n_queries must be in 1..%d", CAB_MAX_QUERIES);
     if (k <= 0 || k > CAB_MAX_K) return fail(idx, CAB_ERR_INVALID, "k must be in 1..%d", CAB_MAX_K);
     if (!std::isfinite(threshold)) return fail(idx, CAB_ERR_INVALID, "threshold must be finite");
     if (path != CAB_PATH_AUTO && path != CAB_PATH_GEMV && path != CAB_PATH_GEMM) return fail(idx, CAB_ERR_INVALID, "unknown path %d", path);
+    if (out && out->loc != CAB_HOST && out->loc != CAB_DEVICE) return fail(idx, CAB_ERR_INVALID, "out_loc");
     for (int i = 0; i < nq; ++i)
         if (!(std::isfinite(w_asr[i]) && std::isfinite(w_audio[i]) && w_asr[i] >= 0 && w_audio[i] >= 0))
             return fail(idx, CAB_ERR_INVALID, "weights must be finite and >= 0");
@@ -451,37 +501,17 @@ static int run_local(cab_index *idx, const float *queries, int queries_loc, cons
     const int batch = use_gemm ? nq : int(std::min<int64_t>(nq, idx->opt_gemv_batch));
     int rc = ensure_workspace(idx, nq, k, n_partials, batch, use_gemm ? gemm_workspace_bytes(nq, k, idx->sm_count) : 0);
     if (rc != CAB_OK) return rc;
+    const float *dq = nullptr;
+    if ((rc = stage_params(idx, queries, queries_loc, w_asr, w_audio, nq, s, &dq))) return rc;
 
-    // host staging block: [queries?][w64 asr][w64 audio][w32 a][w32 b]
-    const size_t qbytes = size_t(nq) * CAB_DIM * 4;
-    const size_t in_bytes = (queries_loc == CAB_HOST ? qbytes : 0) + size_t(nq) * (16 + 8);
-    if ((rc = ensure_pinned(idx, &idx->h_in, &idx->h_in_bytes, in_bytes))) return rc;
-    if (idx->ev_in_pending) { CU(idx, cudaEventSynchronize(idx->ev_in)); idx->ev_in_pending = false; }
-    uint8_t *h = idx->h_in;
-    const float *dq = queries;
-    if (queries_loc == CAB_HOST) {
-        memcpy(h, queries, qbytes);
-        CU(idx, cudaMemcpyAsync(idx->d_queries, h, qbytes, cudaMemcpyHostToDevice, s));
-        dq = idx->d_queries;
-        h += qbytes;
-    }
-    double *h64 = reinterpret_cast<double *>(h);
-    float *h32 = reinterpret_cast<float *>(h + size_t(nq) * 16);
-    for (int i = 0; i < nq; ++i) {
-        h64[i] = w_asr[i]; h64[nq + i] = w_audio[i];
-        const double tot = w_asr[i] + w_audio[i];
-        h32[i] = tot > 0 ? float(w_asr[i] / tot) : 0.f;
-        h32[nq + i] = tot > 0 ? float(w_audio[i] / tot) : 0.f;
-    }
-    CU(idx, cudaMemcpyAsync(idx->d_w64, h64, size_t(nq) * 16, cudaMemcpyHostToDevice, s));
-    CU(idx, cudaMemcpyAsync(idx->d_w32, h32, size_t(nq) * 8, cudaMemcpyHostToDevice, s));
-    CU(idx, cudaEventRecord(idx->ev_in, s));
-    idx->ev_in_pending = true;
-
+    EmitArgs ea{};
+    if (out) ea = make_emit(idx, 1, nq, k, threshold, out->index, out->fusion, out->asr, out->audio,
+                            out->flags, out->count, out->loc);
     idx->timed = false;
     if (idx->size == 0) {
         // nothing to scan: every candidate slot is empty
         CU(idx, cudaMemsetAsync(idx->d_cands, 0xFF, size_t(nq) * k * sizeof(cab_candidate), s));
+        if (out) { ea.cands = idx->d_cands; launch_emit(ea, s); idx->launches += 1; CU(idx, cudaGetLastError()); }
         return CAB_OK;
     }
 
@@ -489,12 +519,12 @@ static int run_local(cab_index *idx, const float *queries, int queries_loc, cons
     sa.asr = idx->asr; sa.audio = idx->audio; sa.flags = idx->flags; sa.n_rows = idx->size;
     sa.dtype = idx->dtype; sa.k = k;
     sa.select_threshold = float(threshold) - 1e-6f;
-    sa.partial_keys = idx->d_partial_keys; sa.partial_count = idx->d_partial_count;
+    sa.partial_keys = idx->d_partial_keys;
     sa.n_partials = n_partials; sa.nonfinite = idx->d_nonfinite;
     FinalizeArgs fa{};
     fa.asr = idx->asr; fa.audio = idx->audio; fa.flags = idx->flags; fa.dtype = idx->dtype;
     fa.row_base = idx->row_base; fa.k = k; fa.partial_keys = idx->d_partial_keys;
-    fa.partial_count = idx->d_partial_count; fa.n_partials = n_partials;
+    fa.n_partials = n_partials;
 
     if (idx->opt_time_kernels) CU(idx, cudaEventRecord(idx->ev_t0, s));
     for (int q0 = 0; q0 < nq; q0 += batch) {
@@ -510,7 +540,18 @@ static int run_local(cab_index *idx, const float *queries, int queries_loc, cons
         }
         if (idx->opt_time_kernels && q0 + batch >= nq) CU(idx, cudaEventRecord(idx->ev_t1, s));
         fa.queries = sa.queries; fa.n_queries = m; fa.cands = idx->d_cands + size_t(q0) * k;
-        launch_finalize(fa, s);
+        if (out) {
+            EmitArgs eb = ea;                           // this batch's slice of the outputs
+            eb.n_queries = m;
+            eb.w_asr = ea.w_asr + q0; eb.w_audio = ea.w_audio + q0;
+            eb.out_index = ea.out_index + size_t(q0) * k; eb.out_fusion = ea.out_fusion + size_t(q0) * k;
+            eb.out_asr = ea.out_asr + size_t(q0) * k; eb.out_audio = ea.out_audio + size_t(q0) * k;
+            eb.out_flags = ea.out_flags + size_t(q0) * k; eb.out_count = ea.out_count + q0;
+            if (q0 + batch < nq) eb.nonfinite_out = nullptr;    // only the last batch reports the flag
+            launch_finalize(fa, &eb, s);
+        } else {
+            launch_finalize(fa, nullptr, s);
+        }
         idx->launches += 2;
     }
     if (idx->opt_time_kernels) idx->timed = true;
@@ -518,35 +559,16 @@ static int run_local(cab_index *idx, const float *queries, int queries_loc, cons
     return CAB_OK;
 }
 
-static int emit_and_return(cab_index *idx, const cab_candidate *cands, int n_lists, int nq, int k,
-                           double threshold, int64_t *out_index, double *out_fusion, float *out_asr,
-                           float *out_audio, uint8_t *out_flags, int32_t *out_count, int out_loc,
-                           cudaStream_t s) {
-    if (out_loc != CAB_HOST && out_loc != CAB_DEVICE) return fail(idx, CAB_ERR_INVALID, "out_loc");
-    if (size_t(n_lists) * k > 1024) return fail(idx, CAB_ERR_INVALID, "n_lists * k must be <= 1024");
-    const OutLayout L = out_layout(nq, k);
-    uint8_t *d = idx->d_out;
-    EmitArgs ea{};
-    ea.cands = cands; ea.n_lists = n_lists; ea.n_queries = nq; ea.k = k;
-    ea.w_asr = idx->d_w64; ea.w_audio = idx->d_w64 + nq; ea.threshold = threshold;
-    const bool dev = out_loc == CAB_DEVICE;
-    ea.out_index = dev && out_index ? out_index : reinterpret_cast<int64_t *>(d + L.index);
-    ea.out_fusion = dev && out_fusion ? out_fusion : reinterpret_cast<double *>(d + L.fusion);
-    ea.out_asr = dev && out_asr ? out_asr : reinterpret_cast<float *>(d + L.asr);
-    ea.out_audio = dev && out_audio ? out_audio : reinterpret_cast<float *>(d + L.audio);
-    ea.out_flags = dev && out_flags ? out_flags : d + L.flags;
-    ea.out_count = dev && out_count ? out_count : reinterpret_cast<int32_t *>(d + L.count);
-    launch_emit(ea, s);
-    idx->launches += 1;
-    CU(idx, cudaGetLastError());
-    if (dev) {
+// Bring the packed output block back to the host (or nothing to do for device outputs).
+static int finish_outputs(cab_index *idx, int nq, int k, const UserOut &o, cudaStream_t s) {
+    if (o.loc == CAB_DEVICE) {
         if (idx->opt_sync) CU(idx, cudaStreamSynchronize(s));
         return CAB_OK;
     }
+    const OutLayout L = out_layout(nq, k);
     int rc = ensure_pinned(idx, &idx->h_out, &idx->h_out_bytes, L.total);
     if (rc != CAB_OK) return rc;
-    CU(idx, cudaMemcpyAsync(d + L.nonfinite, idx->d_nonfinite, sizeof(int), cudaMemcpyDeviceToDevice, s));
-    CU(idx, cudaMemcpyAsync(idx->h_out, d, L.total, cudaMemcpyDeviceToHost, s));
+    CU(idx, cudaMemcpyAsync(idx->h_out, idx->d_out, L.total, cudaMemcpyDeviceToHost, s));
     CU(idx, cudaStreamSynchronize(s));
     idx->ev_in_pending = false;
     const uint8_t *h = idx->h_out;
@@ -556,12 +578,12 @@ static int emit_and_return(cab_index *idx, const cab_candidate *cands, int n_lis
         return fail(idx, CAB_ERR_NONFINITE, "Input contains NaN or infinity (query)");
     }
     const size_t n = size_t(nq) * k;
-    if (out_index) memcpy(out_index, h + L.index, n * 8);
-    if (out_fusion) memcpy(out_fusion, h + L.fusion, n * 8);
-    if (out_asr) memcpy(out_asr, h + L.asr, n * 4);
-    if (out_audio) memcpy(out_audio, h + L.audio, n * 4);
-    if (out_flags) memcpy(out_flags, h + L.flags, n);
-    if (out_count) memcpy(out_count, h + L.count, size_t(nq) * 4);
+    if (o.index) memcpy(o.index, h + L.index, n * 8);
+    if (o.fusion) memcpy(o.fusion, h + L.fusion, n * 8);
+    if (o.asr) memcpy(o.asr, h + L.asr, n * 4);
+    if (o.audio) memcpy(o.audio, h + L.audio, n * 4);
+    if (o.flags) memcpy(o.flags, h + L.flags, n);
+    if (o.count) memcpy(o.count, h + L.count, size_t(nq) * 4);
     return CAB_OK;
 }
 
@@ -571,10 +593,10 @@ int cab_search(cab_index *idx, const float *queries, int queries_loc, const doub
                uint8_t *out_flags, int32_t *out_count, int out_loc, void *stream) {
     CHECK_HANDLE(idx);
     cudaStream_t s = stream ? (cudaStream_t)stream : idx->own_stream;
-    int rc = run_local(idx, queries, queries_loc, w_asr, w_audio, n_queries, k, threshold, path, s);
+    const UserOut o{out_index, out_fusion, out_asr, out_audio, out_flags, out_count, out_loc};
+    int rc = run_local(idx, queries, queries_loc, w_asr, w_audio, n_queries, k, threshold, path, &o, s);
     if (rc != CAB_OK) return rc;
-    return emit_and_return(idx, idx->d_cands, 1, n_queries, k, threshold, out_index, out_fusion,
-                           out_asr, out_audio, out_flags, out_count, out_loc, s);
+    return finish_outputs(idx, n_queries, k, o, s);
 }
 
 int cab_search_candidates(cab_index *idx, const float *queries, int queries_loc,
@@ -583,7 +605,7 @@ int cab_search_candidates(cab_index *idx, const float *queries, int queries_loc,
     CHECK_HANDLE(idx);
     if (!out_device) return fail(idx, CAB_ERR_INVALID, "out_device is null");
     cudaStream_t s = stream ? (cudaStream_t)stream : idx->own_stream;
-    int rc = run_local(idx, queries, queries_loc, w_asr, w_audio, n_queries, k, threshold, path, s);
+    int rc = run_local(idx, queries, queries_loc, w_asr, w_audio, n_queries, k, threshold, path, nullptr, s);
     if (rc != CAB_OK) return rc;
     CU(idx, cudaMemcpyAsync(out_device, idx->d_cands, size_t(n_queries) * k * sizeof(cab_candidate),
                             cudaMemcpyDeviceToDevice, s));
@@ -599,28 +621,30 @@ int cab_merge_candidates(cab_index *idx, const cab_candidate *cands_device, int 
     CHECK_HANDLE(idx);
     if (!cands_device || !w_asr || !w_audio || n_lists <= 0) return fail(idx, CAB_ERR_INVALID, "bad merge arguments");
     if (n_queries <= 0 || n_queries > CAB_MAX_QUERIES || k <= 0 || k > CAB_MAX_K) return fail(idx, CAB_ERR_INVALID, "bad n_queries / k");
+    if (size_t(n_lists) * k > 1024) return fail(idx, CAB_ERR_INVALID, "n_lists * k must be <= 1024");
+    if (out_loc != CAB_HOST && out_loc != CAB_DEVICE) return fail(idx, CAB_ERR_INVALID, "out_loc");
     CU(idx, cudaSetDevice(idx->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : idx->own_stream;
     int rc = ensure_workspace(idx, n_queries, k, 1, 1, 0);
     if (rc != CAB_OK) return rc;
-    if ((rc = ensure_pinned(idx, &idx->h_in, &idx->h_in_bytes, size_t(n_queries) * 16))) return rc;
-    if (idx->ev_in_pending) { CU(idx, cudaEventSynchronize(idx->ev_in)); idx->ev_in_pending = false; }
-    double *h64 = reinterpret_cast<double *>(idx->h_in);
-    for (int i = 0; i < n_queries; ++i) { h64[i] = w_asr[i]; h64[n_queries + i] = w_audio[i]; }
-    CU(idx, cudaMemcpyAsync(idx->d_w64, h64, size_t(n_queries) * 16, cudaMemcpyHostToDevice, s));
-    CU(idx, cudaEventRecord(idx->ev_in, s));
-    idx->ev_in_pending = true;
-    return emit_and_return(idx, cands_device, n_lists, n_queries, k, threshold, out_index, out_fusion,
-                           out_asr, out_audio, out_flags, out_count, out_loc, s);
+    if ((rc = stage_params(idx, nullptr, CAB_DEVICE, w_asr, w_audio, n_queries, s, nullptr))) return rc;
+    const UserOut o{out_index, out_fusion, out_asr, out_audio, out_flags, out_count, out_loc};
+    EmitArgs ea = make_emit(idx, n_lists, n_queries, k, threshold, out_index, out_fusion, out_asr,
+                            out_audio, out_flags, out_count, out_loc);
+    ea.cands = cands_device;
+    launch_emit(ea, s);
+    idx->launches += 1;
+    CU(idx, cudaGetLastError());
+    return finish_outputs(idx, n_queries, k, o, s);
 }
 
 int cab_index_set_option(cab_index *idx, const char *key, int64_t value) {
     CHECK_HANDLE(idx);
     if (!key) return fail(idx, CAB_ERR_INVALID, "null option key");
     std::string k(key);
-    if (k == "gemv_variant") { if (value < 0 || value > 1) return fail(idx, CAB_ERR_INVALID, "gemv_variant in {0,1}"); idx->gemv.variant = int(value); }
+    if (k == "gemv_variant") { if (value != 0) return fail(idx, CAB_ERR_INVALID, "gemv_variant: only 0 (LDG register pipeline) is built"); idx->gemv.variant = int(value); }
     else if (k == "gemv_blocks_per_sm") { if (value < 0 || value > 8) return fail(idx, CAB_ERR_INVALID, "gemv_blocks_per_sm in 0..8"); idx->gemv.blocks_per_sm = int(value); }
-    else if (k == "gemv_unroll") { if (value != 0 && value != 1 && value != 2 && value != 4) return fail(idx, CAB_ERR_INVALID, "gemv_unroll in {0,1,2,4}"); idx->gemv.unroll = int(value); }
+    else if (k == "gemv_unroll") { if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) return fail(idx, CAB_ERR_INVALID, "gemv_unroll in {0,1,2,4,8}"); idx->gemv.unroll = int(value); }
     else if (k == "time_kernels") idx->opt_time_kernels = value != 0;
     else if (k == "sync_after_search") idx->opt_sync = value != 0;
     else if (k == "gemm_min_queries") { if (value < 1) return fail(idx, CAB_ERR_INVALID, "gemm_min_queries >= 1"); idx->opt_gemm_min_queries = value; }

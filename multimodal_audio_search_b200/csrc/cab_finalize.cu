@@ -1,56 +1,148 @@
-// After the scan: (1) finalize -- merge the per-CTA partial top-k lists of one query into its
+// After the scan: (1) finalize -- merge the per-CTA partial top-k slots of one query into its
 // best k rows and re-score those rows (both cosines, fp32) -> cab_candidate records;
 // (2) emit -- from 1..world candidate lists per query compute the reference's float64 fusion
 // score (audio_search.py:656-670), apply the strict float64 threshold (:672), order by
 // (score desc, global index asc) (:685) and write the first k (:699).
+// On a single GPU (one candidate list) emit runs inside the finalize kernel.
 //
-// Both kernels touch O(k) rows per query; they are latency-, not bandwidth-bound, and run as one
-// CTA per query.
+// Both touch O(k) rows per query; they are latency-, not bandwidth-bound, and run as one CTA per
+// query: every global load is issued in parallel (no dependent chains), all selection happens in
+// shared memory.
 #include "cab_internal.h"
 #include "cab_rowdot.cuh"
 
 namespace cab {
 
-constexpr int kFinThreads = 512;
+constexpr int kFinThreads = 1024;
 constexpr int kFinWarps = kFinThreads / 32;
+constexpr int kSortCap = 4096;          // keys in the shared-memory selection buffer
+constexpr int kFinUnroll = 2;           // slots loaded per thread per round
 
+__device__ __forceinline__ uint64_t orderable64(double d) {
+    uint64_t u = (uint64_t)__double_as_longlong(d);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double unorderable64(uint64_t o) {
+    uint64_t u = (o >> 63) ? (o & 0x7FFFFFFFFFFFFFFFull) : ~o;
+    return __longlong_as_double((long long)u);
+}
+
+// audio_search.py:654-672 in float64 with separate multiply / add like CPython.  Returns the
+// orderable score, or 0 when the candidate is not a result.
+__device__ __forceinline__ uint64_t reference_fusion(const cab_candidate &c, double wa, double wb,
+                                                     double threshold) {
+    if (c.index < 0) return 0ull;
+    const double sa = double(c.asr_sim), sb = double(c.audio_sim);
+    double ea = (c.flags & 1u) ? wa : 0.0;
+    double eb = (c.flags & 2u) ? wb : 0.0;
+    const double tot = __dadd_rn(ea, eb);
+    if (!((sa > 0.0 || sb > 0.0) && tot > 0.0)) return 0ull;
+    ea = __ddiv_rn(ea, tot);
+    eb = __ddiv_rn(eb, tot);
+    const double fusion = __dadd_rn(__dmul_rn(ea, sa), __dmul_rn(eb, sb));
+    return fusion > threshold ? orderable64(fusion) : 0ull;
+}
+
+// Block-wide bitonic sort of (score desc, index asc) triples in shared memory.
+__device__ __forceinline__ void block_sort_results(uint64_t *score, int64_t *index, uint16_t *pos, int np2) {
+    for (int size = 2; size <= np2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < np2 / 2; t += blockDim.x) {
+                const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                const bool desc = ((lo & size) == 0);
+                const uint64_t s0 = score[lo], s1 = score[hi];
+                const int64_t i0 = index[lo], i1 = index[hi];
+                const bool lo_below_hi = (s0 < s1) || (s0 == s1 && i0 > i1);
+                if (lo_below_hi == desc && !(s0 == s1 && i0 == i1)) {
+                    score[lo] = s1; score[hi] = s0;
+                    index[lo] = i1; index[hi] = i0;
+                    const uint16_t p = pos[lo]; pos[lo] = pos[hi]; pos[hi] = p;
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void write_results(const EmitArgs &e, int qi, const uint64_t *score,
+                                              const uint16_t *pos, const cab_candidate *cand_of_pos,
+                                              int *s_n) {
+    for (int i = threadIdx.x; i < e.k; i += blockDim.x) {
+        const size_t o = size_t(qi) * e.k + i;
+        if (score[i] != 0ull) {
+            const cab_candidate c = cand_of_pos[pos[i]];
+            e.out_index[o] = c.index;
+            e.out_fusion[o] = unorderable64(score[i]);
+            e.out_asr[o] = c.asr_sim;
+            e.out_audio[o] = c.audio_sim;
+            e.out_flags[o] = uint8_t(c.flags);
+            atomicAdd(s_n, 1);
+        } else {
+            e.out_index[o] = -1;
+            e.out_fusion[o] = 0.0;
+            e.out_asr[o] = 0.f;
+            e.out_audio[o] = 0.f;
+            e.out_flags[o] = 0;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        e.out_count[qi] = *s_n;
+        if (qi == 0 && e.nonfinite_out) { *e.nonfinite_out = *e.nonfinite; }
+    }
+}
+
+// ---- finalize ---------------------------------------------------------------------------------
 template <int DT>
-__global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a) {
+__global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, EmitArgs e) {
     using TR = RowTraits<DT>;
-    __shared__ uint64_t s_keys[kFinWarps][kWarpCap];
-    __shared__ int s_count[kFinWarps];
+    __shared__ uint64_t s_sort[kSortCap];
+    __shared__ cab_candidate s_cand[kMaxK];
+    __shared__ int s_cnt, s_n;
+    __shared__ uint64_t s_bound;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int qi = blockIdx.x;
+    if (threadIdx.x == 0) { s_cnt = 0; s_bound = 0ull; s_n = 0; }
+    __syncthreads();
 
-    WarpTopK top;
-    top.init(s_keys[warp], a.k, 0ull);
-    for (int p = warp; p < a.n_partials; p += kFinWarps) {
-        const size_t list = size_t(qi) * a.n_partials + p;
-        const int c = a.partial_count[list];
-        for (int i = 0; i < c; i += 32) {
-            const bool in = i + lane < c;
-            const uint64_t key = in ? a.partial_keys[list * a.k + i + lane] : 0ull;
-            top.push(in && key > top.bound, key, lane);
+    // Sort the buffer, keep the best k, raise the bound.  Block-uniform.
+    auto trim = [&]() {
+        const int c = s_cnt;
+        int np2 = 64;
+        while (np2 < c) np2 <<= 1;
+        for (int i = c + threadIdx.x; i < np2; i += kFinThreads) s_sort[i] = 0ull;
+        block_sort_desc(s_sort, np2);
+        if (threadIdx.x == 0) {
+            const int kept = c < a.k ? c : a.k;
+            s_cnt = kept;
+            if (kept == a.k) s_bound = s_sort[a.k - 1];
         }
-    }
-    top.compact(lane);
-    if (lane == 0) s_count[warp] = top.count;
-    __syncthreads();
-    if (warp == 0) {
-        for (int w2 = 1; w2 < kFinWarps; ++w2) {
-            const int c2 = s_count[w2];
-            for (int i = 0; i < c2; i += 32) {
-                const bool in = i + lane < c2;
-                const uint64_t key = in ? s_keys[w2][i + lane] : 0ull;
-                top.push(in && key > top.bound, key, lane);
-            }
+        __syncthreads();
+    };
+
+    // ---- stream all partial slots of this query (empty slots hold 0) through the buffer ---------
+    const uint64_t *__restrict__ slots = a.partial_keys + size_t(qi) * a.n_partials * a.k;
+    const int total = a.n_partials * a.k;
+    for (int base = 0; base < total; base += kFinThreads * kFinUnroll) {
+        uint64_t key[kFinUnroll];
+#pragma unroll
+        for (int u = 0; u < kFinUnroll; ++u) {
+            const int i = base + u * kFinThreads + threadIdx.x;
+            key[u] = i < total ? slots[i] : 0ull;
         }
-        top.compact(lane);
-        if (lane == 0) s_count[0] = top.count;
+        const uint64_t bound = s_bound;
+#pragma unroll
+        for (int u = 0; u < kFinUnroll; ++u)
+            if (key[u] > bound) s_sort[atomicAdd(&s_cnt, 1)] = key[u];
+        __syncthreads();
+        const bool full = s_cnt > kSortCap - kFinThreads * kFinUnroll;
+        __syncthreads();                   // everyone has read s_cnt before anyone appends again
+        if (full) trim();
     }
-    __syncthreads();
-    const int n_win = s_count[0];
+    trim();
+    const int n_win = s_cnt;
 
     // ---- re-score the winners: one lane group per row, same operation order as the scan ---------
     float q[TR::NQ];
@@ -62,16 +154,16 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a) {
     for (int i0 = warp * TR::RW; i0 < a.k; i0 += kFinWarps * TR::RW) {
         const int i = i0 + sub;
         const bool have = i < n_win;                       // uniform within a lane group
-        const uint32_t row = have ? key_row(s_keys[0][i]) : 0u;
+        const uint32_t row = have ? key_row(s_sort[i]) : 0u;
         float sa = 0.f, sb = 0.f;
         if (have) {
             const uint4 *pa = A + size_t(row) * TR::CPR + g;
             const uint4 *pb = B + size_t(row) * TR::CPR + g;
+            uint4 ca[3], cb[3];
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                sa = dot_chunk<DT>(pa[TR::G * j], q, j, sa);
-                sb = dot_chunk<DT>(pb[TR::G * j], q, j, sb);
-            }
+            for (int j = 0; j < 3; ++j) { ca[j] = pa[TR::G * j]; cb[j] = pb[TR::G * j]; }
+#pragma unroll
+            for (int j = 0; j < 3; ++j) { sa = dot_chunk<DT>(ca[j], q, j, sa); sb = dot_chunk<DT>(cb[j], q, j, sb); }
         }
         sa = group_sum<DT>(sa);
         sb = group_sum<DT>(sb);
@@ -82,23 +174,42 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a) {
             c.flags = have ? uint32_t(a.flags[row]) : 0u;
             c.pad = 0u;
             out[i] = c;
+            s_cand[i] = c;
         }
     }
+    if (!e.out_index) return;          // sharded search: candidates go to the all-gather
+
+    // ---- fused emit (single candidate list) --------------------------------------------------------
+    __syncthreads();
+    uint64_t *score = s_sort;                                        // reuse: 128 x (8 + 8 + 2) bytes
+    int64_t *index = reinterpret_cast<int64_t *>(s_sort + kMaxK);
+    uint16_t *pos = reinterpret_cast<uint16_t *>(s_sort + 2 * kMaxK);
+    const double wa = e.w_asr[qi], wb = e.w_audio[qi];
+    int np2 = 64;
+    while (np2 < a.k) np2 <<= 1;
+    for (int t = threadIdx.x; t < np2; t += kFinThreads) {
+        uint64_t sc = 0ull;
+        int64_t gi = INT64_MAX;
+        if (t < a.k) {
+            sc = reference_fusion(s_cand[t], wa, wb, e.threshold);
+            if (sc) gi = s_cand[t].index;
+        }
+        score[t] = sc; index[t] = gi; pos[t] = uint16_t(t);
+    }
+    block_sort_results(score, index, pos, np2);
+    write_results(e, qi, score, pos, s_cand, &s_n);
 }
 
-void launch_finalize(const FinalizeArgs &a, cudaStream_t s) {
-    if (a.dtype == CAB_BF16) finalize_kernel<CAB_BF16><<<a.n_queries, kFinThreads, 0, s>>>(a);
-    else finalize_kernel<CAB_F32><<<a.n_queries, kFinThreads, 0, s>>>(a);
+void launch_finalize(const FinalizeArgs &a, const EmitArgs *fused_emit, cudaStream_t s) {
+    EmitArgs e{};
+    if (fused_emit) e = *fused_emit;
+    if (a.dtype == CAB_BF16) finalize_kernel<CAB_BF16><<<a.n_queries, kFinThreads, 0, s>>>(a, e);
+    else finalize_kernel<CAB_F32><<<a.n_queries, kFinThreads, 0, s>>>(a, e);
 }
 
-// ---- emit -------------------------------------------------------------------------------------
+// ---- emit (merge of several candidate lists: sharded search) ---------------------------------------
 constexpr int kEmitThreads = 256;
 constexpr int kEmitMax = 1024;      // >= world(8) x CAB_MAX_K(128)
-
-__device__ __forceinline__ uint64_t orderable64(double d) {
-    uint64_t u = (uint64_t)__double_as_longlong(d);
-    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
-}
 
 __global__ void __launch_bounds__(kEmitThreads) emit_kernel(EmitArgs a) {
     __shared__ uint64_t s_score[kEmitMax];     // orderable float64 fusion score, 0 = not a result
@@ -112,59 +223,28 @@ __global__ void __launch_bounds__(kEmitThreads) emit_kernel(EmitArgs a) {
     while (np2 < n_cand) np2 <<= 1;
     const double wa = a.w_asr[qi], wb = a.w_audio[qi];
     if (threadIdx.x == 0) s_n = 0;
-
+    // candidate t of this query lives at list-major position:
+    auto cand_at = [&](int t) -> const cab_candidate * {
+        const int list = t / a.k, i = t - list * a.k;
+        return a.cands + (size_t(list) * a.n_queries + qi) * a.k + i;
+    };
     for (int t = threadIdx.x; t < np2; t += kEmitThreads) {
         uint64_t sc = 0ull;
         int64_t gi = INT64_MAX;
         if (t < n_cand) {
-            const int list = t / a.k, i = t - list * a.k;
-            const cab_candidate c = a.cands[(size_t(list) * a.n_queries + qi) * a.k + i];
-            if (c.index >= 0) {
-                // audio_search.py:654-672, float64 with separate multiply/add like CPython
-                const double sa = double(c.asr_sim), sb = double(c.audio_sim);
-                double ea = (c.flags & 1u) ? wa : 0.0;
-                double eb = (c.flags & 2u) ? wb : 0.0;
-                const double tot = __dadd_rn(ea, eb);
-                if ((sa > 0.0 || sb > 0.0) && tot > 0.0) {
-                    ea = __ddiv_rn(ea, tot);
-                    eb = __ddiv_rn(eb, tot);
-                    const double fusion = __dadd_rn(__dmul_rn(ea, sa), __dmul_rn(eb, sb));
-                    if (fusion > a.threshold) { sc = orderable64(fusion); gi = c.index; }
-                }
-            }
+            const cab_candidate c = *cand_at(t);
+            sc = reference_fusion(c, wa, wb, a.threshold);
+            if (sc) gi = c.index;
         }
         s_score[t] = sc; s_index[t] = gi; s_pos[t] = uint16_t(t);
     }
-    // bitonic sort, descending by (score, -index)
-    for (int size = 2; size <= np2; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            __syncthreads();
-            for (int t = threadIdx.x; t < np2 / 2; t += kEmitThreads) {
-                const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
-                const bool desc = ((lo & size) == 0);
-                const uint64_t s0 = s_score[lo], s1 = s_score[hi];
-                const int64_t i0 = s_index[lo], i1 = s_index[hi];
-                const bool lo_lt_hi = (s0 < s1) || (s0 == s1 && i0 > i1);   // "lo ranks below hi"
-                if (lo_lt_hi == desc && !(s0 == s1 && i0 == i1)) {
-                    s_score[lo] = s1; s_score[hi] = s0;
-                    s_index[lo] = i1; s_index[hi] = i0;
-                    const uint16_t p = s_pos[lo]; s_pos[lo] = s_pos[hi]; s_pos[hi] = p;
-                }
-            }
-        }
-    }
-    __syncthreads();
+    block_sort_results(s_score, s_index, s_pos, np2);
     for (int i = threadIdx.x; i < a.k; i += kEmitThreads) {
-        const bool res = s_score[i] != 0ull;
         const size_t o = size_t(qi) * a.k + i;
-        if (res) {
-            const int t = s_pos[i];
-            const int list = t / a.k, ii = t - list * a.k;
-            const cab_candidate c = a.cands[(size_t(list) * a.n_queries + qi) * a.k + ii];
-            const uint64_t so = s_score[i];
-            const uint64_t u = (so >> 63) ? (so & 0x7FFFFFFFFFFFFFFFull) : ~so;
+        if (s_score[i] != 0ull) {
+            const cab_candidate c = *cand_at(s_pos[i]);
             a.out_index[o] = c.index;
-            a.out_fusion[o] = __longlong_as_double((long long)u);
+            a.out_fusion[o] = unorderable64(s_score[i]);
             a.out_asr[o] = c.asr_sim;
             a.out_audio[o] = c.audio_sim;
             a.out_flags[o] = uint8_t(c.flags);
@@ -178,7 +258,10 @@ __global__ void __launch_bounds__(kEmitThreads) emit_kernel(EmitArgs a) {
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) a.out_count[qi] = s_n;
+    if (threadIdx.x == 0) {
+        a.out_count[qi] = s_n;
+        if (qi == 0 && a.nonfinite_out) { *a.nonfinite_out = *a.nonfinite; }
+    }
 }
 
 void launch_emit(const EmitArgs &a, cudaStream_t s) {

@@ -8,13 +8,11 @@
 // 1536 B bf16 (+1 flag byte, not counted).  At 6.5 TB/s that is one fp32 row pair every
 // ~70 SM-cycles chip-wide, i.e. ~133 cycles per row per SM: the kernel has ~500 issue slots per
 // row and needs only ~60, so the design goal is purely bytes-in-flight:
-//   variant 0 (this file): persistent CTAs; every warp keeps U row-steps (U*RW rows x 2 corpora x
+//   persistent CTAs; every warp keeps U row-steps (U*RW rows x 2 corpora x
 //     3 x 16 B per lane = 6U independent LDG.128 per lane) in flight in registers, 128-bit
 //     coalesced L1-bypassing loads; a transposing shuffle reduction (12 shuffles per 4 rows
 //     instead of 40) leaves each row's (s_asr, s_audio) in one lane group; fusion in registers;
 //     one compare against the warp's running k-th best rejects almost every row.
-//   variant 1 (cab_gemv_bulk.cu): cp.async.bulk (TMA 1-D) slabs into an mbarrier-guarded smem
-//     ring, consumers read smem.
 #include "cab_internal.h"
 #include "cab_rowdot.cuh"
 
@@ -40,7 +38,7 @@ gemv_scan_kernel(ScanArgs a) {
     constexpr int G = TR::G, RW = TR::RW, CPR = TR::CPR;
     constexpr int kRowsPerIter = U * RW;
     constexpr int kOwnerLanes = G / U;            // lanes sharing one finished row
-    static_assert(U == 1 || U == 2 || U == 4, "U");
+    static_assert(U == 1 || U == 2 || U == 4 || U == 8, "U");
 
     __shared__ uint64_t s_keys[kScanWarps][kWarpCap];
     __shared__ int s_count[kScanWarps];
@@ -138,16 +136,18 @@ gemv_scan_kernel(ScanArgs a) {
         }
         top.compact(lane);
         const size_t list = size_t(qi) * a.n_partials + blockIdx.x;
-        for (int i = lane; i < top.count; i += 32) a.partial_keys[list * a.k + i] = top.buf[i];
-        if (lane == 0) a.partial_count[list] = top.count;
+        for (int i = lane; i < a.k; i += 32) a.partial_keys[list * a.k + i] = i < top.count ? top.buf[i] : 0ull;
     }
 }
 
 // (unroll, blocks/SM) combinations that are instantiated; anything else maps to the nearest.
 static void resolve(const GemvConfig &cfg, int dtype, int *u, int *mb) {
-    (void)dtype;
-    *u = cfg.unroll ? cfg.unroll : 4;
-    *mb = cfg.blocks_per_sm ? cfg.blocks_per_sm : (*u == 4 ? 2 : (*u == 2 ? 3 : 4));
+    // Defaults from the B200 sweep (profiles/r01_gemv_sweep.md): fewer, fatter warps win --
+    // fp32: 1 CTA/SM x 8 warps x 24 LDG.128 per lane (98 KB in flight per SM) = 7.33 TB/s at 10M;
+    // bf16: 2 CTAs/SM x 12 LDG.128 per lane = 7.25 TB/s.
+    *u = cfg.unroll ? cfg.unroll : (dtype == CAB_BF16 ? 2 : 4);
+    *mb = cfg.blocks_per_sm ? cfg.blocks_per_sm : (dtype == CAB_BF16 ? 2 : 1);
+    if (*u == 8) *mb = 1;                     // 48 x LDG.128 per lane: 192 registers of loads
     if (*u == 4 && *mb > 2) *mb = 2;          // 24 x LDG.128 per lane needs > 96 registers
     if (*u == 2 && *mb > 4) *mb = 4;
     if (*mb > 4) *mb = 4;
@@ -162,16 +162,14 @@ int gemv_grid_size(const GemvConfig &cfg, int dtype, int sm_count) {
 template <int DT>
 static void launch_dt(const ScanArgs &a, int u, int mb, dim3 grid, cudaStream_t s) {
 #define CAB_CASE(U_, MB_) if (u == U_ && mb == MB_) { gemv_scan_kernel<DT, U_, MB_><<<grid, kScanThreads, 0, s>>>(a); return; }
-    CAB_CASE(4, 1) CAB_CASE(4, 2)
+    CAB_CASE(8, 1) CAB_CASE(4, 1) CAB_CASE(4, 2)
     CAB_CASE(2, 1) CAB_CASE(2, 2) CAB_CASE(2, 3) CAB_CASE(2, 4)
     CAB_CASE(1, 1) CAB_CASE(1, 2) CAB_CASE(1, 3) CAB_CASE(1, 4)
 #undef CAB_CASE
 }
 
-void launch_gemv_bulk_scan(const ScanArgs &a, const GemvConfig &cfg, int sm_count, cudaStream_t s);
-
 void launch_gemv_scan(const ScanArgs &a, const GemvConfig &cfg, int sm_count, cudaStream_t s) {
-    if (cfg.variant == 1) { launch_gemv_bulk_scan(a, cfg, sm_count, s); return; }
+    (void)sm_count;
     int u, mb;
     resolve(cfg, a.dtype, &u, &mb);
     dim3 grid(a.n_partials, a.n_queries);

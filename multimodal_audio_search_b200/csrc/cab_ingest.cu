@@ -97,16 +97,28 @@ __device__ __forceinline__ float synth_elem(uint32_t row_key, int j) {
     return float(int(s) - 510);
 }
 
-__global__ void __launch_bounds__(256) synth_rows_kernel(SynthParams p, int stream_id, int64_t r0,
-                                                         int64_t n, float *__restrict__ out) {
+// `partial`: rows whose pipeline "failed" (flag bit clear, see synth.row_flags) have no embedding
+// in the reference (None, audio_search.py:344/350) -> an all-zero row here.
+__global__ void __launch_bounds__(256) synth_rows_kernel(SynthParams p, int stream_id, int partial,
+                                                         int64_t r0, int64_t n, float *__restrict__ out) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
     const uint32_t skey = stream_key(p.seed, uint32_t(stream_id));
     const uint32_t qkey = stream_key(p.seed, 2u);
+    const uint32_t fkey = stream_key(p.seed, 3u);
     for (int64_t i = warp; i < n; i += n_warps) {
         const uint64_t r = uint64_t(r0 + i);
         const uint32_t rk = mix32(skey ^ uint32_t(r));
+        if (partial) {
+            const uint32_t hv = mix32(mix32(fkey ^ uint32_t(r))) % 10u;
+            const uint32_t fl = hv == 0u ? 1u : (hv == 1u ? 2u : 3u);
+            if (!(fl & (1u << stream_id))) {
+#pragma unroll
+                for (int c = 0; c < kDim / 32; ++c) out[i * kDim + lane + 32 * c] = 0.f;
+                continue;
+            }
+        }
         float m = 0.f, nn = 1.f;
         uint32_t qrk = 0;
         if (p.n_plants_total) {
@@ -131,12 +143,12 @@ __global__ void __launch_bounds__(256) synth_rows_kernel(SynthParams p, int stre
         }
     }
 }
-void launch_synth_rows(const SynthParams &p, int stream_id, int64_t r0, int64_t n, float *out,
-                       cudaStream_t s) {
+void launch_synth_rows(const SynthParams &p, int stream_id, int partial, int64_t r0, int64_t n,
+                       float *out, cudaStream_t s) {
     if (n <= 0) return;
     int64_t blocks = (n + 7) / 8;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    synth_rows_kernel<<<int(blocks), 256, 0, s>>>(p, stream_id, r0, n, out);
+    synth_rows_kernel<<<int(blocks), 256, 0, s>>>(p, stream_id, partial, r0, n, out);
 }
 
 __global__ void synth_flags_kernel(uint32_t seed, int partial, int64_t r0, int64_t n,

@@ -20,8 +20,8 @@ struct SynthParams {
     uint32_t plants;           // per query
     uint64_t base, inv_stride;
 };
-void launch_synth_rows(const SynthParams &p, int stream_id, int64_t r0, int64_t n, float *out,
-                       cudaStream_t s);
+void launch_synth_rows(const SynthParams &p, int stream_id, int partial, int64_t r0, int64_t n,
+                       float *out, cudaStream_t s);
 void launch_synth_flags(uint32_t seed, int partial, int64_t r0, int64_t n, uint8_t *out,
                         cudaStream_t s);
 void launch_widen_rows(const void *src, int dtype, int64_t r0, int64_t n, float *out,
@@ -40,9 +40,8 @@ struct ScanArgs {
     int n_queries;
     int k;
     float select_threshold;    // fp32 bound used while scanning (slightly below the fp64 one)
-    // outputs: per (query, partial list) sorted keys
+    // outputs: per (query, scan CTA) the CTA's best keys, unused slots = 0
     uint64_t *partial_keys;    // [n_queries][n_partials][k]
-    int32_t *partial_count;    // [n_queries][n_partials]
     int n_partials;            // == grid size of the scan
     int *nonfinite;            // set if a query holds NaN/Inf
 };
@@ -66,11 +65,12 @@ struct FinalizeArgs {
     int n_queries;
     int k;
     const uint64_t *partial_keys;
-    const int32_t *partial_count;
     int n_partials;
     cab_candidate *cands;      // out [n_queries][k], best-first by scan score, index -1 = empty
 };
-void launch_finalize(const FinalizeArgs &a, cudaStream_t s);
+struct EmitArgs;
+// fused_emit != nullptr (single candidate list): the emit stage runs inside the same kernel.
+void launch_finalize(const FinalizeArgs &a, const EmitArgs *fused_emit, cudaStream_t s);
 
 struct EmitArgs {
     const cab_candidate *cands;   // [n_lists][n_queries][k]
@@ -86,6 +86,8 @@ struct EmitArgs {
     float *out_audio;
     uint8_t *out_flags;
     int32_t *out_count;
+    const int *nonfinite;         // device flag set by scan / ingest kernels
+    int *nonfinite_out;           // copy of it next to the outputs (may be null)
 };
 void launch_emit(const EmitArgs &a, cudaStream_t s);
 

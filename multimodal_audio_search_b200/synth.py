@@ -4,7 +4,7 @@ BASELINE.json's configs are all "synthetic unit vectors" libraries; the referenc
 fixtures.  Every element here is a small INTEGER stored as fp32, produced by
 a counter-based 32-bit hash of (seed, stream, global_row, column), so
 
-  * the numpy generator below and the CUDA generator (csrc/synth.cu, `cab_synth_fill`) emit
+  * the numpy generator below and the CUDA generator (csrc/cab_ingest.cu, `cab_index_append_synth`) emit
     bit-identical rows on any machine -- no libm, no float rounding in the generator;
   * any row range [r0, r1) can be generated independently, so a corpus sharded over 1/2/4/8 GPUs
     is the same corpus (SURVEY.md section 8(e));
@@ -173,9 +173,14 @@ def row_flags(seed: int, r0: int, r1: int, partial: bool) -> np.ndarray:
 
 def library(seed: int, n_rows: int, n_queries: int = 1, plants: int = 0, partial: bool = False,
             r0: int = 0, r1: int | None = None, dim: int = DIM):
-    """(asr_rows, audio_rows, flags, spec) for global rows [r0, r1) of an n_rows library."""
+    """(asr_rows, audio_rows, flags, spec) for global rows [r0, r1) of an n_rows library.
+    A pipeline whose flag bit is clear has NO embedding in the reference (`None`,
+    audio_search.py:344/350 -> similarity 0.0 at :640-641): its row is all zeros here."""
     r1 = n_rows if r1 is None else r1
     spec = plant_spec(seed, n_rows, n_queries, plants)
     a = corpus_rows(seed, STREAM_ASR, r0, r1, spec, dim)
     b = corpus_rows(seed, STREAM_AUDIO, r0, r1, spec, dim)
-    return a, b, row_flags(seed, r0, r1, partial), spec
+    f = row_flags(seed, r0, r1, partial)
+    a[(f & FLAG_ASR) == 0] = 0.0
+    b[(f & FLAG_AUDIO) == 0] = 0.0
+    return a, b, f, spec

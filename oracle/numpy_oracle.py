@@ -142,3 +142,20 @@ def search_chunked(q, row_source, n_rows: int, w_asr: float, w_audio: float, k: 
     return (idx, np.array([-t[0] for t in best], dtype=np.float64),
             np.array([t[2] for t in best], dtype=np.float32),
             np.array([t[3] for t in best], dtype=np.float32))
+
+
+def search_prenormalized(qn, asr_n, audio_n, flags, w_asr: float, w_audio: float, k: int = 10,
+                         threshold: float = 0.1):
+    """CPU-baseline variant used by bench.py: rows L2-normalised ONCE at ingest (what the engine
+    does) instead of on every call like the reference; per query 2 sgemv + fusion + threshold +
+    top-k (argpartition, then a stable sort of the k survivors).  Same results as `search`."""
+    sa = asr_n @ qn
+    sb = audio_n @ qn
+    fusion, _, _ = fuse(sa, sb, flags, w_asr, w_audio)
+    passing = np.nonzero(fusion > threshold)[0]
+    if len(passing) > k:
+        part = passing[np.argpartition(-fusion[passing], k - 1)[:k]]
+        kth = fusion[part].min()
+        passing = passing[fusion[passing] >= kth]
+    order = passing[np.argsort(-fusion[passing], kind="stable")][:k]
+    return order.astype(np.int64), fusion[order], sa[order], sb[order]
