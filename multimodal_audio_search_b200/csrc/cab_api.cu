@@ -55,6 +55,7 @@ struct cab_index {
     // options
     GemvConfig gemv{0, 0, 0};
     int64_t opt_time_kernels = 0, opt_sync = 0, opt_gemm_min_queries = 64, opt_gemv_batch = 32;
+    int64_t opt_finalize_general = 0;
     int64_t launches = 0;
     std::string err;
     int sticky = CAB_OK;
@@ -524,7 +525,7 @@ static int run_local(cab_index *idx, const float *queries, int queries_loc, cons
     FinalizeArgs fa{};
     fa.asr = idx->asr; fa.audio = idx->audio; fa.flags = idx->flags; fa.dtype = idx->dtype;
     fa.row_base = idx->row_base; fa.k = k; fa.partial_keys = idx->d_partial_keys;
-    fa.n_partials = n_partials;
+    fa.n_partials = n_partials; fa.force_general = int(idx->opt_finalize_general);
 
     if (idx->opt_time_kernels) CU(idx, cudaEventRecord(idx->ev_t0, s));
     for (int q0 = 0; q0 < nq; q0 += batch) {
@@ -647,6 +648,7 @@ int cab_index_set_option(cab_index *idx, const char *key, int64_t value) {
     else if (k == "gemv_unroll") { if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) return fail(idx, CAB_ERR_INVALID, "gemv_unroll in {0,1,2,4,8}"); idx->gemv.unroll = int(value); }
     else if (k == "time_kernels") idx->opt_time_kernels = value != 0;
     else if (k == "sync_after_search") idx->opt_sync = value != 0;
+    else if (k == "finalize_general") idx->opt_finalize_general = value != 0;
     else if (k == "gemm_min_queries") { if (value < 1) return fail(idx, CAB_ERR_INVALID, "gemm_min_queries >= 1"); idx->opt_gemm_min_queries = value; }
     else if (k == "gemv_batch") { if (value < 1 || value > 64) return fail(idx, CAB_ERR_INVALID, "gemv_batch in 1..64"); idx->opt_gemv_batch = value; }
     else return fail(idx, CAB_ERR_INVALID, "unknown option '%s'", key);
@@ -661,6 +663,7 @@ int64_t cab_index_get_option(const cab_index *idx, const char *key) {
     if (k == "gemv_unroll") return idx->gemv.unroll;
     if (k == "time_kernels") return idx->opt_time_kernels;
     if (k == "sync_after_search") return idx->opt_sync;
+    if (k == "finalize_general") return idx->opt_finalize_general;
     if (k == "gemm_min_queries") return idx->opt_gemm_min_queries;
     if (k == "gemv_batch") return idx->opt_gemv_batch;
     if (k == "sm_count") return idx->sm_count;

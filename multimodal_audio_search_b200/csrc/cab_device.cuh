@@ -59,7 +59,8 @@ __device__ __forceinline__ float fuse32(float sa, float sb, uint32_t flags, Scan
     float ea = (flags & 1u) ? ((flags & 2u) ? w.wa : 1.0f) : 0.0f;
     float eb = (flags & 2u) ? ((flags & 1u) ? w.wb : 1.0f) : 0.0f;
     float f = fmaf(ea, sa, eb * sb);
-    return (flags & 3u) ? f : -INFINITY;
+    // :654 gate (redundant for the reference's positive threshold, kept for any threshold)
+    return ((flags & 3u) && (sa > 0.f || sb > 0.f)) ? f : -INFINITY;
 }
 
 // ---- bitonic sort (descending) of a power-of-two array of u64 keys in shared memory, by one

@@ -17,6 +17,8 @@ constexpr int kFinThreads = 1024;
 constexpr int kFinWarps = kFinThreads / 32;
 constexpr int kSortCap = 4096;          // keys in the shared-memory selection buffer
 constexpr int kFinUnroll = 2;           // slots loaded per thread per round
+constexpr int kMaxHeads = 1024;         // scan CTAs (partial lists) the fast path can rank
+constexpr int kRankMax = 2048;          // survivors the fast path ranks by counting
 
 __device__ __forceinline__ uint64_t orderable64(double d) {
     uint64_t u = (uint64_t)__double_as_longlong(d);
@@ -65,46 +67,19 @@ __device__ __forceinline__ void block_sort_results(uint64_t *score, int64_t *ind
     __syncthreads();
 }
 
-__device__ __forceinline__ void write_results(const EmitArgs &e, int qi, const uint64_t *score,
-                                              const uint16_t *pos, const cab_candidate *cand_of_pos,
-                                              int *s_n) {
-    for (int i = threadIdx.x; i < e.k; i += blockDim.x) {
-        const size_t o = size_t(qi) * e.k + i;
-        if (score[i] != 0ull) {
-            const cab_candidate c = cand_of_pos[pos[i]];
-            e.out_index[o] = c.index;
-            e.out_fusion[o] = unorderable64(score[i]);
-            e.out_asr[o] = c.asr_sim;
-            e.out_audio[o] = c.audio_sim;
-            e.out_flags[o] = uint8_t(c.flags);
-            atomicAdd(s_n, 1);
-        } else {
-            e.out_index[o] = -1;
-            e.out_fusion[o] = 0.0;
-            e.out_asr[o] = 0.f;
-            e.out_audio[o] = 0.f;
-            e.out_flags[o] = 0;
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        e.out_count[qi] = *s_n;
-        if (qi == 0 && e.nonfinite_out) { *e.nonfinite_out = *e.nonfinite; }
-    }
-}
-
 // ---- finalize ---------------------------------------------------------------------------------
 template <int DT>
 __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, EmitArgs e) {
     using TR = RowTraits<DT>;
     __shared__ uint64_t s_sort[kSortCap];
     __shared__ cab_candidate s_cand[kMaxK];
-    __shared__ int s_cnt, s_n;
+    __shared__ uint64_t s_head[kMaxHeads];
+    __shared__ int s_cnt;
     __shared__ uint64_t s_bound;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int qi = blockIdx.x;
-    if (threadIdx.x == 0) { s_cnt = 0; s_bound = 0ull; s_n = 0; }
+    if (threadIdx.x == 0) { s_cnt = 0; s_bound = 0ull; }
     __syncthreads();
 
     // Sort the buffer, keep the best k, raise the bound.  Block-uniform.
@@ -122,26 +97,90 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, E
         __syncthreads();
     };
 
-    // ---- stream all partial slots of this query (empty slots hold 0) through the buffer ---------
     const uint64_t *__restrict__ slots = a.partial_keys + size_t(qi) * a.n_partials * a.k;
     const int total = a.n_partials * a.k;
-    for (int base = 0; base < total; base += kFinThreads * kFinUnroll) {
-        uint64_t key[kFinUnroll];
-#pragma unroll
-        for (int u = 0; u < kFinUnroll; ++u) {
-            const int i = base + u * kFinThreads + threadIdx.x;
-            key[u] = i < total ? slots[i] : 0ull;
-        }
-        const uint64_t bound = s_bound;
-#pragma unroll
-        for (int u = 0; u < kFinUnroll; ++u)
-            if (key[u] > bound) s_sort[atomicAdd(&s_cnt, 1)] = key[u];
+
+    // Warp-aggregated append of passing keys into s_sort; returns false if the buffer overflowed.
+    auto append = [&](bool pass, uint64_t key) {
+        const unsigned m = __ballot_sync(kFull, pass);
+        if (m == 0) return;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&s_cnt, __popc(m));
+        base = __shfl_sync(kFull, base, 0);
+        const int pos = base + __popc(m & ((1u << lane) - 1u));
+        if (pass && pos < kSortCap) s_sort[pos] = key;
+    };
+
+    // ---- fast path (small k): each scan CTA's slots are sorted, so the k-th largest list HEAD is
+    // a lower bound on the global k-th best; only keys >= it can be results.  Typically ~2k keys
+    // survive; they are ranked by counting (no sort, no barriers inside).
+    bool done = false;
+    if (a.n_partials <= kMaxHeads && !a.force_general) {
+        for (int j = threadIdx.x; j < a.n_partials; j += kFinThreads) s_head[j] = slots[size_t(j) * a.k];
         __syncthreads();
-        const bool full = s_cnt > kSortCap - kFinThreads * kFinUnroll;
-        __syncthreads();                   // everyone has read s_cnt before anyone appends again
-        if (full) trim();
+        for (int j = threadIdx.x; j < a.n_partials; j += kFinThreads) {
+            const uint64_t h = s_head[j];
+            int r = 0;
+            for (int t = 0; t < a.n_partials; ++t) r += s_head[t] > h;
+            if (h != 0ull && r == a.k - 1) s_bound = h - 1;         // keys > bound <=> keys >= H_k
+        }
+        __syncthreads();
+        const uint64_t bound = s_bound;                              // 0 if fewer than k non-empty lists
+        for (int base = 0; base < total; base += kFinThreads) {
+            const int i = base + threadIdx.x;
+            const uint64_t key = i < total ? slots[i] : 0ull;
+            append(key > bound, key);
+        }
+        __syncthreads();
+        const int S = s_cnt;
+        if (S <= kRankMax) {
+            uint64_t mine[kRankMax / kFinThreads];
+            int rank[kRankMax / kFinThreads];
+#pragma unroll
+            for (int u = 0; u < kRankMax / kFinThreads; ++u) {
+                const int i = threadIdx.x + u * kFinThreads;
+                mine[u] = i < S ? s_sort[i] : 0ull;
+                rank[u] = 0;
+            }
+            for (int t = 0; t < S; ++t) {
+                const uint64_t x = s_sort[t];
+#pragma unroll
+                for (int u = 0; u < kRankMax / kFinThreads; ++u) rank[u] += x > mine[u];
+            }
+            __syncthreads();                                         // all reads of s_sort done
+#pragma unroll
+            for (int u = 0; u < kRankMax / kFinThreads; ++u)
+                if (threadIdx.x + u * kFinThreads < S && rank[u] < a.k) s_sort[rank[u]] = mine[u];
+            if (threadIdx.x == 0) s_cnt = S < a.k ? S : a.k;
+            __syncthreads();
+            done = true;
+        } else {
+            __syncthreads();
+            if (threadIdx.x == 0) { s_cnt = 0; s_bound = 0ull; }
+            __syncthreads();
+        }
     }
-    trim();
+
+    // ---- general path: stream all slots (empty slots hold 0) through the buffer, sorting and
+    // trimming to the best k whenever it fills ----------------------------------------------------
+    if (!done) {
+        for (int base = 0; base < total; base += kFinThreads * kFinUnroll) {
+            uint64_t key[kFinUnroll];
+#pragma unroll
+            for (int u = 0; u < kFinUnroll; ++u) {
+                const int i = base + u * kFinThreads + threadIdx.x;
+                key[u] = i < total ? slots[i] : 0ull;
+            }
+            const uint64_t bound = s_bound;
+#pragma unroll
+            for (int u = 0; u < kFinUnroll; ++u) append(key[u] > bound, key[u]);
+            __syncthreads();
+            const bool full = s_cnt > kSortCap - kFinThreads * kFinUnroll;
+            __syncthreads();               // everyone has read s_cnt before anyone appends again
+            if (full) trim();
+        }
+        trim();
+    }
     const int n_win = s_cnt;
 
     // ---- re-score the winners: one lane group per row, same operation order as the scan ---------
@@ -179,25 +218,43 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, E
     }
     if (!e.out_index) return;          // sharded search: candidates go to the all-gather
 
-    // ---- fused emit (single candidate list) --------------------------------------------------------
+    // ---- fused emit (single candidate list): rank the <= k candidates by counting ----------------
     __syncthreads();
-    uint64_t *score = s_sort;                                        // reuse: 128 x (8 + 8 + 2) bytes
-    int64_t *index = reinterpret_cast<int64_t *>(s_sort + kMaxK);
-    uint16_t *pos = reinterpret_cast<uint16_t *>(s_sort + 2 * kMaxK);
+    uint64_t *score = s_sort;                                        // reuse the selection buffer
     const double wa = e.w_asr[qi], wb = e.w_audio[qi];
-    int np2 = 64;
-    while (np2 < a.k) np2 <<= 1;
-    for (int t = threadIdx.x; t < np2; t += kFinThreads) {
-        uint64_t sc = 0ull;
-        int64_t gi = INT64_MAX;
-        if (t < a.k) {
-            sc = reference_fusion(s_cand[t], wa, wb, e.threshold);
-            if (sc) gi = s_cand[t].index;
+    const int t = threadIdx.x;
+    if (t < a.k) score[t] = reference_fusion(s_cand[t], wa, wb, e.threshold);
+    __syncthreads();
+    const size_t o0 = size_t(qi) * e.k;
+    if (t < a.k) {
+        const uint64_t sc = score[t];
+        const int64_t gi = s_cand[t].index;
+        int rank = 0, n_res = 0;
+        for (int j = 0; j < a.k; ++j) {
+            const uint64_t sj = score[j];
+            n_res += sj != 0ull;
+            rank += (sj > sc) || (sj == sc && sj != 0ull && s_cand[j].index < gi);
         }
-        score[t] = sc; index[t] = gi; pos[t] = uint16_t(t);
+        if (sc != 0ull) {                                            // (score desc, index asc), :685
+            const cab_candidate c = s_cand[t];
+            e.out_index[o0 + rank] = c.index;
+            e.out_fusion[o0 + rank] = unorderable64(sc);
+            e.out_asr[o0 + rank] = c.asr_sim;
+            e.out_audio[o0 + rank] = c.audio_sim;
+            e.out_flags[o0 + rank] = uint8_t(c.flags);
+        }
+        if (t >= n_res) {                                            // pad beyond the results
+            e.out_index[o0 + t] = -1;
+            e.out_fusion[o0 + t] = 0.0;
+            e.out_asr[o0 + t] = 0.f;
+            e.out_audio[o0 + t] = 0.f;
+            e.out_flags[o0 + t] = 0;
+        }
+        if (t == 0) {
+            e.out_count[qi] = n_res;
+            if (qi == 0 && e.nonfinite_out) *e.nonfinite_out = *e.nonfinite;
+        }
     }
-    block_sort_results(score, index, pos, np2);
-    write_results(e, qi, score, pos, s_cand, &s_n);
 }
 
 void launch_finalize(const FinalizeArgs &a, const EmitArgs *fused_emit, cudaStream_t s) {

@@ -67,6 +67,7 @@ struct FinalizeArgs {
     const uint64_t *partial_keys;
     int n_partials;
     cab_candidate *cands;      // out [n_queries][k], best-first by scan score, index -1 = empty
+    int force_general;         // test hook: skip the head-bound fast path
 };
 struct EmitArgs;
 // fused_emit != nullptr (single candidate list): the emit stage runs inside the same kernel.

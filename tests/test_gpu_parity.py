@@ -151,6 +151,38 @@ def test_scan_variants_agree():
         assert key == base
 
 
+def test_finalize_paths_agree():
+    """Head-bound fast path vs the general streaming/bitonic path of the finalize kernel."""
+    seed, n = 91, 200000
+    for dtype in ("fp32", "bf16"):
+        idx = SegmentIndex(dtype)
+        idx.append_synth(seed, n, 0, n, n_queries=3, plants=150, partial=True)
+        q = synth.raw_queries(seed, 0, 3)
+        for k in (1, 10, 37, 100, 128):
+            for thr in (0.1, -1.0):                 # -1: every row passes -> full candidate lists
+                idx.set_option("finalize_general", 0)
+                fast = idx.search(q, [0.5, 0.2, 0.8], [0.5, 0.8, 0.2], k=k, threshold=thr)
+                idx.set_option("finalize_general", 1)
+                gen = idx.search(q, [0.5, 0.2, 0.8], [0.5, 0.8, 0.2], k=k, threshold=thr)
+                assert fast.indices.tolist() == gen.indices.tolist(), (dtype, k, thr)
+                assert fast.fusion.tolist() == gen.fusion.tolist()
+                assert fast.count.tolist() == gen.count.tolist()
+                if thr < 0:
+                    assert (fast.count == k).all()
+
+
+def test_threshold_minus_one_matches_oracle():
+    """With the threshold out of the way every row competes: exercises full partial lists."""
+    seed, n, k = 17, 30000, 64
+    a, b, f, _ = synth.library(seed, n, 1, 0, True)
+    q = synth.raw_queries(seed, 0, 1)
+    o = no.search(q[0], a, b, f, 0.4, 0.6, k=k, threshold=-1.0)
+    idx = _index_from(a, b, f)
+    res = idx.search(q, 0.4, 0.6, k=k, threshold=-1.0)
+    gi, gf, _, _, _ = result_row(res)
+    assert_topk_matches(gi, gf, o, FP32_TOL, threshold=-1.0)
+
+
 def test_top100_peel_case(search_cases):
     case = [c for c in search_cases if c.get("k") == 100][0]
     a, b, f, _ = synth.library(case["seed"], case["n_rows"], 1, case["plants"], case["partial"])
