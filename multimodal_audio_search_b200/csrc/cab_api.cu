@@ -413,10 +413,10 @@ static int ensure_dev(cab_index *idx, T **p, size_t *have, size_t want) {
     return CAB_OK;
 }
 
-static int ensure_workspace(cab_index *idx, int nq, int k, int n_partials, int scan_batch, size_t gemm_ws) {
+static int ensure_workspace(cab_index *idx, int nq, int k, int n_partials, int scan_batch, int slots, size_t gemm_ws) {
     int rc;
     if ((rc = ensure_dev(idx, &idx->d_params, &idx->sz_params, size_t(nq) * (24 + CAB_DIM * 4)))) return rc;
-    if ((rc = ensure_dev(idx, &idx->d_partial_keys, &idx->sz_pkeys, size_t(scan_batch) * n_partials * k * 8))) return rc;
+    if ((rc = ensure_dev(idx, &idx->d_partial_keys, &idx->sz_pkeys, size_t(scan_batch) * n_partials * slots * 8))) return rc;
     if ((rc = ensure_dev(idx, &idx->d_cands, &idx->sz_cands, size_t(nq) * k * sizeof(cab_candidate)))) return rc;
     if ((rc = ensure_dev(idx, &idx->d_out, &idx->d_out_bytes, out_layout(nq, k).total))) return rc;
     if (gemm_ws && (rc = ensure_dev(idx, &idx->d_gemm_ws, &idx->d_gemm_ws_bytes, gemm_ws))) return rc;
@@ -499,8 +499,9 @@ static int run_local(cab_index *idx, const float *queries, int queries_loc, cons
     CU(idx, cudaSetDevice(idx->device));
     const int n_partials = use_gemm ? gemm_partials_per_query(idx->sm_count)
                                     : gemv_grid_size(idx->gemv, idx->dtype, idx->sm_count);
-    const int batch = use_gemm ? nq : int(std::min<int64_t>(nq, idx->opt_gemv_batch));
-    int rc = ensure_workspace(idx, nq, k, n_partials, batch, use_gemm ? gemm_workspace_bytes(nq, k, idx->sm_count) : 0);
+    const int batch = use_gemm ? std::min(nq, kGemmQueriesPerPass) : int(std::min<int64_t>(nq, idx->opt_gemv_batch));
+    int rc = ensure_workspace(idx, nq, k, n_partials, use_gemm ? kGemmQueriesPerPass : batch,
+                              use_gemm ? kGemmListCap : k, use_gemm ? gemm_workspace_bytes(nq, k, idx->sm_count) : 0);
     if (rc != CAB_OK) return rc;
     const float *dq = nullptr;
     if ((rc = stage_params(idx, queries, queries_loc, w_asr, w_audio, nq, s, &dq))) return rc;
@@ -526,6 +527,8 @@ static int run_local(cab_index *idx, const float *queries, int queries_loc, cons
     fa.asr = idx->asr; fa.audio = idx->audio; fa.flags = idx->flags; fa.dtype = idx->dtype;
     fa.row_base = idx->row_base; fa.k = k; fa.partial_keys = idx->d_partial_keys;
     fa.n_partials = n_partials; fa.force_general = int(idx->opt_finalize_general);
+    fa.slot_stride = use_gemm ? kGemmListCap : k;
+    fa.counts = use_gemm ? reinterpret_cast<const int32_t *>(idx->d_gemm_ws) : nullptr;
 
     if (idx->opt_time_kernels) CU(idx, cudaEventRecord(idx->ev_t0, s));
     for (int q0 = 0; q0 < nq; q0 += batch) {
@@ -626,7 +629,7 @@ int cab_merge_candidates(cab_index *idx, const cab_candidate *cands_device, int 
     if (out_loc != CAB_HOST && out_loc != CAB_DEVICE) return fail(idx, CAB_ERR_INVALID, "out_loc");
     CU(idx, cudaSetDevice(idx->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : idx->own_stream;
-    int rc = ensure_workspace(idx, n_queries, k, 1, 1, 0);
+    int rc = ensure_workspace(idx, n_queries, k, 1, 1, k, 0);
     if (rc != CAB_OK) return rc;
     if ((rc = stage_params(idx, nullptr, CAB_DEVICE, w_asr, w_audio, n_queries, s, nullptr))) return rc;
     const UserOut o{out_index, out_fusion, out_asr, out_audio, out_flags, out_count, out_loc};

@@ -97,8 +97,9 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, E
         __syncthreads();
     };
 
-    const uint64_t *__restrict__ slots = a.partial_keys + size_t(qi) * a.n_partials * a.k;
-    const int total = a.n_partials * a.k;
+    const uint64_t *__restrict__ slots = a.partial_keys + size_t(qi) * a.n_partials * a.slot_stride;
+    const int total = a.n_partials * a.slot_stride;
+    const int32_t *__restrict__ counts = a.counts ? a.counts + size_t(qi) * a.n_partials : nullptr;
 
     // Warp-aggregated append of passing keys into s_sort; returns false if the buffer overflowed.
     auto append = [&](bool pass, uint64_t key) {
@@ -115,8 +116,8 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, E
     // a lower bound on the global k-th best; only keys >= it can be results.  Typically ~2k keys
     // survive; they are ranked by counting (no sort, no barriers inside).
     bool done = false;
-    if (a.n_partials <= kMaxHeads && !a.force_general) {
-        for (int j = threadIdx.x; j < a.n_partials; j += kFinThreads) s_head[j] = slots[size_t(j) * a.k];
+    if (a.n_partials <= kMaxHeads && !a.force_general && !counts) {
+        for (int j = threadIdx.x; j < a.n_partials; j += kFinThreads) s_head[j] = slots[size_t(j) * a.slot_stride];
         __syncthreads();
         for (int j = threadIdx.x; j < a.n_partials; j += kFinThreads) {
             const uint64_t h = s_head[j];
@@ -169,7 +170,9 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, E
 #pragma unroll
             for (int u = 0; u < kFinUnroll; ++u) {
                 const int i = base + u * kFinThreads + threadIdx.x;
-                key[u] = i < total ? slots[i] : 0ull;
+                bool in = i < total;
+                if (in && counts) { const int list = i / a.slot_stride; in = i - list * a.slot_stride < counts[list]; }
+                key[u] = in ? slots[i] : 0ull;
             }
             const uint64_t bound = s_bound;
 #pragma unroll

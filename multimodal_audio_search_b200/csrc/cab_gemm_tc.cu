@@ -1,14 +1,427 @@
-// Batched path (>= 64 queries): tcgen05 / TMEM GEMM with fused weighting + top-k epilogue.
-// (under construction -- reports "not built" until the kernel lands)
+// Batched path (>= 64 queries, bf16 storage): dense contraction on the 5th-gen tensor cores.
+//
+//   scores_asr  [256 queries x 128 rows] = Q[256 x 384] . A_tile[128 x 384]^T      (bf16 x bf16 -> fp32)
+//   scores_audio[256 queries x 128 rows] = Q[256 x 384] . B_tile[128 x 384]^T
+//
+// replaces, for a batch of queries, the per-segment loop of search_with_fusion
+// (audio_search.py:639-682); weighting, threshold pruning and the running top-k are fused into
+// the epilogue so no score is ever written to memory (256 x 10M scores would be 10 GB).
+//
+// Mapping to sm_100a:
+//   * one persistent CTA PAIR per two SMs (cluster 2x1x1, 74 pairs), tcgen05.mma.cta_group::2 with
+//     M = 256 (128 queries per CTA), N = 128 corpus rows per tile (64 rows staged by each CTA),
+//     K = 384 as 24 MMAs of K = 16.  The pair reads each corpus row exactly once: HBM traffic is
+//     the algorithmic 1536 B per segment per pass of 256 queries.
+//   * operands staged by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle) -- the 128 queries of
+//     each CTA stay resident in shared memory (96 KB), corpus k-blocks (64 rows x 128 B = 8 KB)
+//     flow through a 12-stage mbarrier ring (96 KB in flight per SM);
+//   * accumulators in TMEM: 2 stages x 2 corpora x 128 columns = all 512 columns, so the MMAs of
+//     tile i+1 overlap the epilogue of tile i;
+//   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane of the pair's
+//     leader CTA) + TMEM allocator, warps 2..5 = epilogue.  An epilogue thread owns one TMEM lane
+//     = one query: it reads the two score rows with tcgen05.ld, fuses them with the row flags,
+//     compares with its private running bound (one compare rejects almost every segment) and
+//     appends survivors to its private candidate list in global memory (L2 resident); a full
+//     list is compacted warp-cooperatively (bitonic sort in shared memory, keep k).
+//   Roofline: 2 x 2 x 384 flop per (query, segment); at 256 queries the kernel needs 256 flop per
+//   corpus byte, i.e. it sits on the HBM/tensor ridge.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
 #include <string>
 
+#include "cab_device.cuh"
 #include "cab_internal.h"
 
 namespace cab {
-bool gemm_path_available() { return false; }
-int gemm_partials_per_query(int sm_count) { return sm_count; }
-size_t gemm_workspace_bytes(int, int, int) { return 0; }
-void launch_gemm_scan(const ScanArgs &, int, void *, size_t, cudaStream_t, std::string *err) {
-    if (err) *err = "tensor-core path not built";
+
+// ---- shapes --------------------------------------------------------------------------------------
+constexpr int kTileRows = 128;                 // corpus rows per tile (N of the MMA), per CTA pair
+constexpr int kHalfRows = kTileRows / 2;       // rows staged by each CTA
+constexpr int kQPerCta = 128;                  // queries (M rows) per CTA
+constexpr int kKBlock = 64;                    // bf16 elements per 128-byte swizzle row
+constexpr int kNumKBlocks = kDim / kKBlock;    // 6
+constexpr int kUmmaK = 16;
+constexpr int kStages = 12;                    // ring of 8 KB corpus k-blocks
+constexpr uint32_t kStageBytes = kHalfRows * kKBlock * 2;          // 8192
+constexpr uint32_t kQBlockBytes = kQPerCta * kKBlock * 2;          // 16384
+constexpr int kTmemCols = 512;
+constexpr int kGemmThreads = 192;              // 6 warps
+constexpr int kEpiWarp0 = 2;
+
+// smem layout (dynamic, 1024-byte aligned)
+constexpr uint32_t kOffQ = 0;
+constexpr uint32_t kOffRing = kOffQ + kNumKBlocks * kQBlockBytes;                  // 98304
+constexpr uint32_t kOffScratch = kOffRing + kStages * kStageBytes;                 // 196608
+constexpr uint32_t kOffFlags = kOffScratch + 4 * kWarpCap * 8;                     // + 8 KB
+constexpr uint32_t kOffBars = kOffFlags + 2 * kTileRows;                           // 2 x 128 flag bytes
+constexpr uint32_t kNumBars = 2 * kStages + 4 + 1;
+constexpr uint32_t kOffTmemPtr = kOffBars + kNumBars * 8;
+constexpr uint32_t kGemmSmemBytes = kOffTmemPtr + 16 + 1024;                       // + alignment slack
+
+constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;   // L2 cache hints (createpolicy encodings)
+constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_rank0(uint32_t addr) {      // same smem offset in CTA rank 0 of the cluster
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(0)); return r;
 }
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_bar) : "memory");
+}
+// Bounded wait: a protocol bug must surface as an error (trap), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int *status, int code) {
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+        if (clock64() - t0 > 4000000000ll) {           // ~2 s
+            if (status) atomicExch(status, code);
+            __threadfence_system();
+            asm volatile("trap;");
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, uint32_t leader_bar,
+                                                 int c0, int c1, uint64_t hint) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+                 " [%0], [%1, {%3, %4}], [%2], %5;"
+                 :: "r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "l"(hint) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {       // arrives on `bar` in both CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start address >> 4 | LBO (16 B) | SBO = 8 rows x 128 B = 1024 | version 1 | SWIZZLE_128B.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= uint64_t((smem_addr >> 4) & 0x3FFF);
+    d |= uint64_t(1) << 16;                    // leading byte offset (unused for swizzled K-major)
+    d |= uint64_t(1024 >> 4) << 32;            // stride byte offset
+    d |= uint64_t(1) << 46;                    // descriptor version (Blackwell)
+    d |= uint64_t(2) << 61;                    // SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: D = fp32, A = B = bf16, both K-major, M = 256 (pair), N = 128.
+constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(kTileRows >> 3) << 17) | (uint32_t(256 >> 4) << 24);
+
+// ---- query preparation: normalise like sklearn normalize(X) and round to bf16, zero-pad to 256 -----
+__global__ void __launch_bounds__(256) prep_queries_kernel(const float *__restrict__ q_raw, int n_queries,
+                                                           __nv_bfloat16 *__restrict__ out, int *__restrict__ nonfinite) {
+    const int lane = threadIdx.x & 31;
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= kGemmQueriesPerPass) return;
+    float v[kDim / 32];
+    float ss = 0.f;
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < kDim / 32; ++i) {
+        v[i] = row < n_queries ? q_raw[size_t(row) * kDim + lane + 32 * i] : 0.f;
+        bad |= !isfinite(v[i]);
+        ss = fmaf(v[i], v[i], ss);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(kFull, ss, o);
+    if (__any_sync(kFull, bad) || !isfinite(ss)) { if (lane == 0) *nonfinite = 1; }
+    float norm = sqrtf(ss);
+    if (norm == 0.f) norm = 1.f;
+#pragma unroll
+    for (int i = 0; i < kDim / 32; ++i) out[size_t(row) * kDim + lane + 32 * i] = __float2bfloat16_rn(v[i] / norm);
+}
+
+// ---- the scan ----------------------------------------------------------------------------------------
+struct GemmParams {
+    const uint8_t *flags;
+    int64_t n_rows;
+    const float *wa32, *wb32;      // [n_queries]
+    int n_queries;
+    int k;
+    float select_threshold;
+    uint64_t *lists;               // [256 queries][n_pairs][kGemmListCap]
+    int32_t *counts;               // [256 queries][n_pairs]
+    int n_pairs;
+    int *status;                   // != 0: protocol timeout code
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_asr,
+                 const __grid_constant__ CUtensorMap map_audio, GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment (SWIZZLE_128B atoms); identical offset in both CTAs of the pair.
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta_rank = cluster_ctarank();
+    const bool leader = cta_rank == 0;
+    const int pair = blockIdx.x >> 1;
+
+    const uint32_t bar0 = smem_base + kOffBars;
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (kStages + s); };
+    auto tmem_full_bar = [&](int t) { return bar0 + 8u * (2 * kStages + t); };
+    auto tmem_empty_bar = [&](int t) { return bar0 + 8u * (2 * kStages + 2 + t); };
+    const uint32_t q_bar = bar0 + 8u * (2 * kStages + 4);
+    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(smem + kOffTmemPtr);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int t = 0; t < 2; ++t) { mbar_init(tmem_full_bar(t), 1); mbar_init(tmem_empty_bar(t), 2 * 128); }
+        mbar_init(q_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {                                   // TMEM: all 512 columns of both SMs of the pair
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(tmem_holder)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    const int64_t n_tiles = (p.n_rows + kTileRows - 1) / kTileRows;
+
+    if (warp == 0) {
+        // ===== TMA producer (one lane in each CTA): own 128 queries once, then own half of every tile
+        if (elect_one()) {
+            const uint32_t q_bar_leader = mapa_rank0(q_bar);
+            if (leader) mbar_expect_tx(q_bar, 2 * kNumKBlocks * kQBlockBytes);
+            for (int kb = 0; kb < kNumKBlocks; ++kb)
+                tma_load_2d_pair(smem_base + kOffQ + kb * kQBlockBytes, &map_q, q_bar_leader, kb * kKBlock,
+                                 int(cta_rank) * kQPerCta, kEvictLast);
+            uint32_t n = 0;
+            for (int64_t tile = pair; tile < n_tiles; tile += p.n_pairs) {
+                const int row0 = int(tile * kTileRows) + int(cta_rank) * kHalfRows;
+                for (int c = 0; c < 2; ++c) {
+                    const CUtensorMap *map = c == 0 ? &map_asr : &map_audio;
+                    for (int kb = 0; kb < kNumKBlocks; ++kb, ++n) {
+                        const int s = n % kStages;
+                        const uint32_t ph = (n / kStages) & 1u;
+                        mbar_wait(empty_bar(s), ph ^ 1u, p.status, 1);
+                        if (leader) mbar_expect_tx(full_bar(s), 2 * kStageBytes);
+                        tma_load_2d_pair(smem_base + kOffRing + s * kStageBytes, map, mapa_rank0(full_bar(s)),
+                                         kb * kKBlock, row0, kEvictFirst);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one lane of the leader CTA drives the tensor cores of both SMs
+        if (leader && elect_one()) {
+            mbar_wait(q_bar, 0, p.status, 2);
+            tc_fence_after();
+            uint32_t n = 0, it = 0;
+            for (int64_t tile = pair; tile < n_tiles; tile += p.n_pairs, ++it) {
+                const uint32_t t = it & 1u, tph = (it >> 1) & 1u;
+                mbar_wait(tmem_empty_bar(t), tph ^ 1u, p.status, 3);
+                tc_fence_after();
+                for (int c = 0; c < 2; ++c) {
+                    const uint32_t d_tmem = tmem_base + t * 256u + uint32_t(c) * 128u;
+                    for (int kb = 0; kb < kNumKBlocks; ++kb, ++n) {
+                        const int s = n % kStages;
+                        const uint32_t ph = (n / kStages) & 1u;
+                        mbar_wait(full_bar(s), ph, p.status, 4);
+                        tc_fence_after();
+                        const uint64_t a0 = umma_desc(smem_base + kOffQ + kb * kQBlockBytes);
+                        const uint64_t b0 = umma_desc(smem_base + kOffRing + s * kStageBytes);
+#pragma unroll
+                        for (int k = 0; k < kKBlock / kUmmaK; ++k)          // +32 bytes per K step
+                            tc_mma_pair(d_tmem, a0 + uint64_t(2 * k), b0 + uint64_t(2 * k), kInstrDesc,
+                                        (kb | k) != 0 ? 1u : 0u);
+                        tc_commit_pair(empty_bar(s));                       // frees the stage in both CTAs
+                    }
+                }
+                tc_commit_pair(tmem_full_bar(t));                           // accumulators ready, both CTAs
+            }
+        }
+    } else {
+        // ===== epilogue: thread <-> TMEM lane <-> query
+        const int ew = warp & 3;                              // TMEM lane quarter this warp may access
+        const int qloc = ew * 32 + lane;
+        const int q = int(cta_rank) * kQPerCta + qloc;        // query index within this pass
+        const bool q_valid = q < p.n_queries;
+        const int et = (warp - kEpiWarp0) * 32 + lane;        // 0..127, for cooperative flag loads
+        ScanWeights w{0.f, 0.f};
+        if (q_valid) { w.wa = p.wa32[q]; w.wb = p.wb32[q]; }
+        uint64_t bound = q_valid ? bound_key(p.select_threshold) : ~0ull;
+        int cnt = 0;
+        uint64_t *list = p.lists + (size_t(q) * p.n_pairs + pair) * kGemmListCap;
+        uint64_t *scratch = reinterpret_cast<uint64_t *>(smem + kOffScratch) + (warp - kEpiWarp0) * kWarpCap;
+        uint8_t *s_flags = smem + kOffFlags;
+        const uint32_t lane_addr = tmem_base + (uint32_t(ew * 32) << 16);
+        const uint32_t tmem_empty_leader0 = mapa_rank0(tmem_empty_bar(0));
+        const uint32_t tmem_empty_leader1 = mapa_rank0(tmem_empty_bar(1));
+
+        uint32_t it = 0;
+        for (int64_t tile = pair; tile < n_tiles; tile += p.n_pairs, ++it) {
+            const uint32_t t = it & 1u, tph = (it >> 1) & 1u;
+            const int64_t row0 = tile * kTileRows;
+            {   // row flags of this tile (0 beyond the end of the library => row skipped)
+                const int64_t r = row0 + et;
+                s_flags[t * kTileRows + et] = r < p.n_rows ? p.flags[r] : uint8_t(0);
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(tmem_full_bar(t), tph, p.status, 5);
+            tc_fence_after();
+#pragma unroll 1
+            for (int chunk = 0; chunk < kTileRows / 32; ++chunk) {
+                uint32_t va[32], vb[32];
+                tc_ld32(lane_addr + t * 256u + uint32_t(chunk * 32), va);
+                tc_ld32(lane_addr + t * 256u + 128u + uint32_t(chunk * 32), vb);
+                tc_wait_ld();
+                const uint32_t *fl4 = reinterpret_cast<const uint32_t *>(s_flags + t * kTileRows + chunk * 32);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const uint32_t fl = (fl4[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+                    const float fused = fuse32(__uint_as_float(va[j]), __uint_as_float(vb[j]), fl, w);
+                    const uint64_t key = make_key(fused, uint32_t(row0) + uint32_t(chunk * 32 + j));
+                    if (key > bound) list[cnt++] = key;
+                }
+                // A list that could overflow during the next chunk is compacted by the whole warp.
+                unsigned need = __ballot_sync(kFull, cnt > kGemmListCap - 32);
+                while (need) {
+                    const int src = __ffs(need) - 1;
+                    need &= need - 1;
+                    const uint64_t *lp = reinterpret_cast<const uint64_t *>(
+                        __shfl_sync(kFull, reinterpret_cast<unsigned long long>(list), src));
+                    const int c = __shfl_sync(kFull, cnt, src);
+                    __syncwarp();
+                    for (int i = lane; i < kWarpCap; i += 32) scratch[i] = i < c ? lp[i] : 0ull;
+                    warp_sort_desc<kWarpCap>(scratch, lane);
+                    uint64_t *lw = const_cast<uint64_t *>(lp);
+                    for (int i = lane; i < p.k; i += 32) lw[i] = scratch[i];
+                    const uint64_t kth = scratch[p.k - 1];
+                    __syncwarp();
+                    if (lane == src) { cnt = p.k; if (kth > bound) bound = kth; }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive_cluster(t == 0 ? tmem_empty_leader0 : tmem_empty_leader1);
+        }
+        if (q < kGemmQueriesPerPass) p.counts[size_t(q) * p.n_pairs + pair] = q_valid ? cnt : 0;
+    }
+
+    // ---- teardown: everyone (both CTAs) done before TMEM is released -------------------------------
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+// [rows x 384] bf16 row-major, box = 64 elements (128 B) x box_rows, 128-byte swizzle, zero OOB fill.
+static bool make_map(CUtensorMap *m, const void *base, uint64_t rows, uint32_t box_rows, std::string *err) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { *err = "cuTensorMapEncodeTiled is not available from the driver"; return false; }
+    cuuint64_t dims[2] = {cuuint64_t(kDim), rows};
+    cuuint64_t strides[1] = {cuuint64_t(kDim) * 2};
+    cuuint32_t box[2] = {cuuint32_t(kKBlock), box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { *err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r)); return false; }
+    return true;
+}
+
+bool gemm_path_available() { return true; }
+int gemm_partials_per_query(int sm_count) { return sm_count / 2; }
+
+// workspace: [counts 256 x n_pairs int32][bf16 queries 256 x 384][status int]
+static size_t ws_counts_bytes(int sm_count) { return ((size_t(kGemmQueriesPerPass) * (sm_count / 2) * 4 + 255) / 256) * 256; }
+static size_t ws_queries_bytes() { return size_t(kGemmQueriesPerPass) * kDim * 2; }
+size_t gemm_workspace_bytes(int, int, int sm_count) { return ws_counts_bytes(sm_count) + ws_queries_bytes() + 256; }
+
+void launch_gemm_scan(const ScanArgs &a, int sm_count, void *workspace, size_t workspace_bytes,
+                      cudaStream_t s, std::string *err) {
+    if (a.dtype != CAB_BF16) { *err = "tensor-core scan needs bf16 rows"; return; }
+    if (a.n_queries < 1 || a.n_queries > kGemmQueriesPerPass) { *err = "tensor-core scan takes 1..256 queries per pass"; return; }
+    if (workspace_bytes < gemm_workspace_bytes(a.n_queries, a.k, sm_count)) { *err = "tensor-core workspace too small"; return; }
+    uint8_t *ws = static_cast<uint8_t *>(workspace);
+    int32_t *counts = reinterpret_cast<int32_t *>(ws);
+    __nv_bfloat16 *qb = reinterpret_cast<__nv_bfloat16 *>(ws + ws_counts_bytes(sm_count));
+    int *status = reinterpret_cast<int *>(ws + ws_counts_bytes(sm_count) + ws_queries_bytes());
+
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmSmemBytes));
+        if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return; }
+        attr_done = true;
+    }
+    CUtensorMap mq, ma, mb;
+    if (!make_map(&mq, qb, kGemmQueriesPerPass, kQPerCta, err)) return;
+    if (!make_map(&ma, a.asr, uint64_t(a.n_rows), kHalfRows, err)) return;
+    if (!make_map(&mb, a.audio, uint64_t(a.n_rows), kHalfRows, err)) return;
+
+    cudaMemsetAsync(status, 0, sizeof(int), s);
+    prep_queries_kernel<<<kGemmQueriesPerPass / 8, 256, 0, s>>>(a.queries, a.n_queries, qb, a.nonfinite);
+
+    GemmParams p{};
+    p.flags = a.flags; p.n_rows = a.n_rows; p.wa32 = a.wa32; p.wb32 = a.wb32; p.n_queries = a.n_queries;
+    p.k = a.k; p.select_threshold = a.select_threshold; p.lists = a.partial_keys; p.counts = counts;
+    p.n_pairs = sm_count / 2; p.status = status;
+    gemm_scan_kernel<<<2 * p.n_pairs, kGemmThreads, kGemmSmemBytes, s>>>(mq, ma, mb, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) *err = std::string("gemm_scan_kernel launch: ") + cudaGetErrorString(e);
+}
+
 }  // namespace cab

@@ -41,8 +41,10 @@ struct ScanArgs {
     int k;
     float select_threshold;    // fp32 bound used while scanning (slightly below the fp64 one)
     // outputs: per (query, scan CTA) the CTA's best keys, unused slots = 0
-    uint64_t *partial_keys;    // [n_queries][n_partials][k]
-    int n_partials;            // == grid size of the scan
+    uint64_t *partial_keys;    // [n_queries][n_partials][k]            (GEMV)
+                               // [n_queries][n_partials][kGemmListCap] (GEMM, with counts)
+    int32_t *partial_counts;   // GEMM only: [n_queries][n_partials]
+    int n_partials;            // == grid size of the scan (GEMV) / number of CTA pairs (GEMM)
     int *nonfinite;            // set if a query holds NaN/Inf
 };
 struct GemvConfig {
@@ -54,6 +56,10 @@ struct GemvConfig {
 int gemv_grid_size(const GemvConfig &cfg, int dtype, int sm_count);
 void launch_gemv_scan(const ScanArgs &a, const GemvConfig &cfg, int sm_count, cudaStream_t s);
 
+// ---- tensor-core scan (cab_gemm_tc.cu) -----------------------------------------------------------
+constexpr int kGemmListCap = 256;       // slots per (CTA pair, query) candidate list
+constexpr int kGemmQueriesPerPass = 256;
+
 // ---- finalize + emit (cab_finalize.cu) ----------------------------------------------------------
 struct FinalizeArgs {
     const void *asr;
@@ -64,8 +70,14 @@ struct FinalizeArgs {
     const float *queries;
     int n_queries;
     int k;
+    // Partial lists of query q: n_partials lists of slot_stride slots at
+    //   partial_keys + (q * n_partials + list) * slot_stride.
+    // counts == nullptr: lists are sorted descending and unused slots hold 0 (GEMV scan);
+    // counts != nullptr: list holds counts[q * n_partials + list] unsorted keys (GEMM scan).
     const uint64_t *partial_keys;
+    const int32_t *counts;
     int n_partials;
+    int slot_stride;
     cab_candidate *cands;      // out [n_queries][k], best-first by scan score, index -1 = empty
     int force_general;         // test hook: skip the head-bound fast path
 };
