@@ -183,6 +183,7 @@ def main():
     ap.add_argument("--workload", default="1m_fp32_q1_top10", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--option", action="append", default=[], help="key=value engine option")
+    ap.add_argument("--threshold", type=float, default=0.1, help="relevance threshold (reference: 0.1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -224,18 +225,18 @@ def main():
     def step_device(i):
         sl = slice(i * nq, (i + 1) * nq)
         if world == 1:
-            return idx.search(q_dev[sl], wa_all[sl], wb_all[sl], k=k, path=path)
-        c = idx.search_candidates(q_dev[sl], wa_all[sl], wb_all[sl], k=k, path=path)
+            return idx.search(q_dev[sl], wa_all[sl], wb_all[sl], k=k, path=path, threshold=args.threshold)
+        c = idx.search_candidates(q_dev[sl], wa_all[sl], wb_all[sl], k=k, path=path, threshold=args.threshold)
         dist.all_gather_into_tensor(gathered, c)
-        return idx.merge_candidates(gathered, wa_all[sl], wb_all[sl], k=k, to_host=False)
+        return idx.merge_candidates(gathered, wa_all[sl], wb_all[sl], k=k, threshold=args.threshold, to_host=False)
 
     def step_host(i):
         sl = slice(i * nq, (i + 1) * nq)
         if world == 1:
-            return idx.search(q_host[sl], wa_all[sl], wb_all[sl], k=k, path=path)
-        c = idx.search_candidates(q_host[sl], wa_all[sl], wb_all[sl], k=k, path=path)
+            return idx.search(q_host[sl], wa_all[sl], wb_all[sl], k=k, path=path, threshold=args.threshold)
+        c = idx.search_candidates(q_host[sl], wa_all[sl], wb_all[sl], k=k, path=path, threshold=args.threshold)
         dist.all_gather_into_tensor(gathered, c)
-        return idx.merge_candidates(gathered, wa_all[sl], wb_all[sl], k=k, to_host=True)
+        return idx.merge_candidates(gathered, wa_all[sl], wb_all[sl], k=k, threshold=args.threshold, to_host=True)
 
     def barrier():
         if world > 1:
@@ -315,7 +316,7 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if dtype == "fp32" else "bf16 storage, f32 accumulate", "data": "synthetic (integer-hash rows, planted neighbours)",
             "config": {"workload": args.workload, "segments_per_gpu": n_rows, "global_segments": n_total,
-                       "queries_per_step": nq, "k": k, "path": path, "threshold": 0.1,
+                       "queries_per_step": nq, "k": k, "path": path, "threshold": args.threshold,
                        "l2": "inputs larger than L2 (corpus bytes per GPU >> 126 MB)",
                        "exchange": "none" if world == 1 else "all_gather of per-shard top-k (24 B x k x Q per rank) + device merge",
                        "value_definition": "queries/s x global_segments/1e6"},

@@ -9,14 +9,17 @@
 //
 // Mapping to sm_100a:
 //   * one persistent CTA PAIR per two SMs (cluster 2x1x1, 74 pairs), tcgen05.mma.cta_group::2 with
-//     M = 256 (128 queries per CTA), N = 128 corpus rows per tile (64 rows staged by each CTA),
-//     K = 384 as 24 MMAs of K = 16.  The pair reads each corpus row exactly once: HBM traffic is
-//     the algorithmic 1536 B per segment per pass of 256 queries.
+//     M = 256 (128 queries per CTA) and N = 256 = BOTH corpora of a 128-segment tile in one
+//     instruction: each CTA stages [64 ASR rows | 64 audio rows] of its half of the tile as one
+//     128-row B operand, so one accumulator holds s_asr and s_audio side by side and the query
+//     operand is read once for both.  K = 384 as 24 MMAs of K = 16 per tile.  The pair reads each
+//     corpus row exactly once: HBM traffic is the algorithmic 1536 B per segment per pass.
 //   * operands staged by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle) -- the 128 queries of
-//     each CTA stay resident in shared memory (96 KB), corpus k-blocks (64 rows x 128 B = 8 KB)
-//     flow through a 12-stage mbarrier ring (96 KB in flight per SM);
-//   * accumulators in TMEM: 2 stages x 2 corpora x 128 columns = all 512 columns, so the MMAs of
-//     tile i+1 overlap the epilogue of tile i;
+//     each CTA stay resident in shared memory (96 KB), corpus k-blocks (2 x 64 rows x 128 B =
+//     16 KB) flow through a 7-stage mbarrier ring (112 KB in flight per SM);
+//   * accumulators in TMEM: 2 stages x 256 columns = all 512 columns, so the MMAs of tile i+1
+//     overlap the epilogue of tile i.  Column map of a stage: [0,64) s_asr and [64,128) s_audio of
+//     the leader CTA's 64 segments, [128,192) / [192,256) the same for the peer CTA's 64 segments;
 //   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane of the pair's
 //     leader CTA) + TMEM allocator, warps 2..5 = epilogue.  An epilogue thread owns one TMEM lane
 //     = one query: it reads the two score rows with tcgen05.ld, fuses them with the row flags,
@@ -42,19 +45,21 @@ constexpr int kQPerCta = 128;                  // queries (M rows) per CTA
 constexpr int kKBlock = 64;                    // bf16 elements per 128-byte swizzle row
 constexpr int kNumKBlocks = kDim / kKBlock;    // 6
 constexpr int kUmmaK = 16;
-constexpr int kStages = 12;                    // ring of 8 KB corpus k-blocks
-constexpr uint32_t kStageBytes = kHalfRows * kKBlock * 2;          // 8192
+constexpr int kStages = 7;                     // ring of 16 KB k-blocks ([ASR half | audio half])
+constexpr uint32_t kCorpusBytes = kHalfRows * kKBlock * 2;         // 8192: one corpus, one k-block, this CTA's rows
+constexpr uint32_t kStageBytes = 2 * kCorpusBytes;                 // 16384
 constexpr uint32_t kQBlockBytes = kQPerCta * kKBlock * 2;          // 16384
 constexpr int kTmemCols = 512;
 constexpr int kGemmThreads = 192;              // 6 warps
 constexpr int kEpiWarp0 = 2;
+constexpr int kLevels = 64;                    // score levels of the shared per-query histogram
+constexpr float kLevelStep = 0.004f;
 
 // smem layout (dynamic, 1024-byte aligned)
 constexpr uint32_t kOffQ = 0;
 constexpr uint32_t kOffRing = kOffQ + kNumKBlocks * kQBlockBytes;                  // 98304
 constexpr uint32_t kOffScratch = kOffRing + kStages * kStageBytes;                 // 196608
-constexpr uint32_t kOffFlags = kOffScratch + 4 * kWarpCap * 8;                     // + 8 KB
-constexpr uint32_t kOffBars = kOffFlags + 2 * kTileRows;                           // 2 x 128 flag bytes
+constexpr uint32_t kOffBars = kOffScratch + 4 * kWarpCap * 8;                      // + 8 KB sort scratch
 constexpr uint32_t kNumBars = 2 * kStages + 4 + 1;
 constexpr uint32_t kOffTmemPtr = kOffBars + kNumBars * 8;
 constexpr uint32_t kGemmSmemBytes = kOffTmemPtr + 16 + 1024;                       // + alignment slack
@@ -83,7 +88,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_bar) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(cluster_bar) : "memory");
 }
 // Bounded wait: a protocol bug must surface as an error (trap), never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int *status, int code) {
@@ -140,8 +145,9 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
     d |= uint64_t(2) << 61;                    // SWIZZLE_128B
     return d;
 }
-// kind::f16 instruction descriptor: D = fp32, A = B = bf16, both K-major, M = 256 (pair), N = 128.
-constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(kTileRows >> 3) << 17) | (uint32_t(256 >> 4) << 24);
+// kind::f16 instruction descriptor: D = fp32, A = B = bf16, both K-major, M = 256 (pair), N = 256.
+constexpr uint32_t kUmmaN = 2 * kTileRows;        // 256: [ASR | audio] x [leader | peer] halves
+constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(kUmmaN >> 3) << 17) | (uint32_t(256 >> 4) << 24);
 
 // ---- query preparation: normalise like sklearn normalize(X) and round to bf16, zero-pad to 256 -----
 __global__ void __launch_bounds__(256) prep_queries_kernel(const float *__restrict__ q_raw, int n_queries,
@@ -179,6 +185,10 @@ struct GemmParams {
     int32_t *counts;               // [256 queries][n_pairs]
     int n_pairs;
     int *status;                   // != 0: protocol timeout code
+    // Cross-CTA bound sharing: levels[q][j] counts the candidates of query q pushed (by any CTA)
+    // with fused score in [thr + j*kLevelStep, thr + (j+1)*kLevelStep).  If the counts of levels
+    // >= j sum to k or more, the global k-th best score is >= thr + j*kLevelStep: a safe bound.
+    int32_t *levels;               // [256 queries][kLevels]
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
@@ -204,7 +214,7 @@ gemm_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int t = 0; t < 2; ++t) { mbar_init(tmem_full_bar(t), 1); mbar_init(tmem_empty_bar(t), 2 * 128); }
+        for (int t = 0; t < 2; ++t) { mbar_init(tmem_full_bar(t), 1); mbar_init(tmem_empty_bar(t), 2 * 4); }
         mbar_init(q_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -232,16 +242,15 @@ gemm_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             uint32_t n = 0;
             for (int64_t tile = pair; tile < n_tiles; tile += p.n_pairs) {
                 const int row0 = int(tile * kTileRows) + int(cta_rank) * kHalfRows;
-                for (int c = 0; c < 2; ++c) {
-                    const CUtensorMap *map = c == 0 ? &map_asr : &map_audio;
-                    for (int kb = 0; kb < kNumKBlocks; ++kb, ++n) {
-                        const int s = n % kStages;
-                        const uint32_t ph = (n / kStages) & 1u;
-                        mbar_wait(empty_bar(s), ph ^ 1u, p.status, 1);
-                        if (leader) mbar_expect_tx(full_bar(s), 2 * kStageBytes);
-                        tma_load_2d_pair(smem_base + kOffRing + s * kStageBytes, map, mapa_rank0(full_bar(s)),
-                                         kb * kKBlock, row0, kEvictFirst);
-                    }
+                for (int kb = 0; kb < kNumKBlocks; ++kb, ++n) {
+                    const int s = n % kStages;
+                    const uint32_t ph = (n / kStages) & 1u;
+                    mbar_wait(empty_bar(s), ph ^ 1u, p.status, 1);
+                    if (leader) mbar_expect_tx(full_bar(s), 2 * kStageBytes);
+                    const uint32_t dst = smem_base + kOffRing + s * kStageBytes;
+                    const uint32_t bar = mapa_rank0(full_bar(s));
+                    tma_load_2d_pair(dst, &map_asr, bar, kb * kKBlock, row0, kEvictFirst);
+                    tma_load_2d_pair(dst + kCorpusBytes, &map_audio, bar, kb * kKBlock, row0, kEvictFirst);
                 }
             }
         }
@@ -255,67 +264,142 @@ gemm_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 const uint32_t t = it & 1u, tph = (it >> 1) & 1u;
                 mbar_wait(tmem_empty_bar(t), tph ^ 1u, p.status, 3);
                 tc_fence_after();
-                for (int c = 0; c < 2; ++c) {
-                    const uint32_t d_tmem = tmem_base + t * 256u + uint32_t(c) * 128u;
-                    for (int kb = 0; kb < kNumKBlocks; ++kb, ++n) {
-                        const int s = n % kStages;
-                        const uint32_t ph = (n / kStages) & 1u;
-                        mbar_wait(full_bar(s), ph, p.status, 4);
-                        tc_fence_after();
-                        const uint64_t a0 = umma_desc(smem_base + kOffQ + kb * kQBlockBytes);
-                        const uint64_t b0 = umma_desc(smem_base + kOffRing + s * kStageBytes);
+                const uint32_t d_tmem = tmem_base + t * 256u;
+                for (int kb = 0; kb < kNumKBlocks; ++kb, ++n) {
+                    const int s = n % kStages;
+                    const uint32_t ph = (n / kStages) & 1u;
+                    mbar_wait(full_bar(s), ph, p.status, 4);
+                    tc_fence_after();
+                    const uint64_t a0 = umma_desc(smem_base + kOffQ + kb * kQBlockBytes);
+                    const uint64_t b0 = umma_desc(smem_base + kOffRing + s * kStageBytes);
 #pragma unroll
-                        for (int k = 0; k < kKBlock / kUmmaK; ++k)          // +32 bytes per K step
-                            tc_mma_pair(d_tmem, a0 + uint64_t(2 * k), b0 + uint64_t(2 * k), kInstrDesc,
-                                        (kb | k) != 0 ? 1u : 0u);
-                        tc_commit_pair(empty_bar(s));                       // frees the stage in both CTAs
-                    }
+                    for (int k = 0; k < kKBlock / kUmmaK; ++k)              // +32 bytes per K step
+                        tc_mma_pair(d_tmem, a0 + uint64_t(2 * k), b0 + uint64_t(2 * k), kInstrDesc,
+                                    (kb | k) != 0 ? 1u : 0u);
+                    tc_commit_pair(empty_bar(s));                           // frees the stage in both CTAs
                 }
                 tc_commit_pair(tmem_full_bar(t));                           // accumulators ready, both CTAs
             }
         }
     } else {
-        // ===== epilogue: thread <-> TMEM lane <-> query
+        // ===== epilogue: thread <-> TMEM lane <-> query.  The four warps never synchronise with each
+        // other: each keeps the tile's 128 row flags in registers (lane l holds rows 4l..4l+3).
         const int ew = warp & 3;                              // TMEM lane quarter this warp may access
         const int qloc = ew * 32 + lane;
         const int q = int(cta_rank) * kQPerCta + qloc;        // query index within this pass
         const bool q_valid = q < p.n_queries;
-        const int et = (warp - kEpiWarp0) * 32 + lane;        // 0..127, for cooperative flag loads
         ScanWeights w{0.f, 0.f};
         if (q_valid) { w.wa = p.wa32[q]; w.wb = p.wb32[q]; }
         uint64_t bound = q_valid ? bound_key(p.select_threshold) : ~0ull;
         int cnt = 0;
         uint64_t *list = p.lists + (size_t(q) * p.n_pairs + pair) * kGemmListCap;
         uint64_t *scratch = reinterpret_cast<uint64_t *>(smem + kOffScratch) + (warp - kEpiWarp0) * kWarpCap;
-        uint8_t *s_flags = smem + kOffFlags;
         const uint32_t lane_addr = tmem_base + (uint32_t(ew * 32) << 16);
         const uint32_t tmem_empty_leader0 = mapa_rank0(tmem_empty_bar(0));
         const uint32_t tmem_empty_leader1 = mapa_rank0(tmem_empty_bar(1));
+        const bool thr_nonneg = p.select_threshold >= 0.f;    // then the :654 gate is redundant
+
+        // flags of rows 4*lane .. 4*lane+3 of a tile, 0 for rows beyond the library
+        auto load_flags = [&](int64_t tile) -> uint32_t {
+            const int64_t r = tile * kTileRows + 4 * lane;
+            if (tile >= n_tiles || r >= p.n_rows) return 0u;
+            uint32_t wd = *reinterpret_cast<const uint32_t *>(p.flags + r);   // capacity is a multiple of 4 rows
+            const int64_t left = p.n_rows - r;
+            if (left < 4) wd &= (1u << (8 * int(left))) - 1u;
+            return wd;
+        };
+        // Push one (already fused) candidate; called with warp-divergent predicates.
+        int32_t *my_levels = p.levels + size_t(q_valid ? q : 0) * kLevels;
+        auto push = [&](float fused, uint32_t row) {
+            const uint64_t key = make_key(fused, row);
+            if (key > bound) {
+                list[cnt++] = key;
+                int lvl = int((fused - p.select_threshold) * (1.0f / kLevelStep));
+                lvl = lvl < 0 ? 0 : (lvl > kLevels - 1 ? kLevels - 1 : lvl);
+                atomicAdd(my_levels + lvl, 1);                                 // RED, no return value
+            }
+        };
+        // Levels of the query owned by lane (it & 31): lane l holds levels l and 32 + l.
+        const int q_warp0 = int(cta_rank) * kQPerCta + ew * 32;
+        auto load_levels = [&](uint32_t it_, int &lo, int &hi) {
+            const int qr = q_warp0 + int(it_ & 31u);
+            const int32_t *lp = p.levels + size_t(qr < p.n_queries ? qr : 0) * kLevels;
+            lo = __ldcg(lp + lane);
+            hi = __ldcg(lp + 32 + lane);
+        };
+        int lv_lo, lv_hi;
+        load_levels(0, lv_lo, lv_hi);
 
         uint32_t it = 0;
+        uint32_t flag_word = load_flags(pair);
         for (int64_t tile = pair; tile < n_tiles; tile += p.n_pairs, ++it) {
             const uint32_t t = it & 1u, tph = (it >> 1) & 1u;
-            const int64_t row0 = tile * kTileRows;
-            {   // row flags of this tile (0 beyond the end of the library => row skipped)
-                const int64_t r = row0 + et;
-                s_flags[t * kTileRows + et] = r < p.n_rows ? p.flags[r] : uint8_t(0);
+            const uint32_t row0 = uint32_t(tile * kTileRows);
+            const uint32_t fw = flag_word;
+            flag_word = load_flags(tile + p.n_pairs);                          // prefetch the next tile's flags
+            const bool fast = thr_nonneg && __all_sync(kFull, fw == 0x03030303u);
+            {   // refresh the bound of lane (it & 31)'s query from the shared level histogram
+                int s_hi = lv_hi, s_lo = lv_lo;                                // inclusive suffix sums over lanes
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int a = __shfl_down_sync(kFull, s_hi, o), b = __shfl_down_sync(kFull, s_lo, o);
+                    if (lane + o < 32) { s_hi += a; s_lo += b; }
+                }
+                s_lo += __shfl_sync(kFull, s_hi, 0);
+                const unsigned b_hi = __ballot_sync(kFull, s_hi >= p.k), b_lo = __ballot_sync(kFull, s_lo >= p.k);
+                const int lvl = b_hi ? 32 + (31 - __clz(b_hi)) : (b_lo ? 31 - __clz(b_lo) : -1);
+                if (lvl >= 0 && lane == int(it & 31u)) {
+                    const uint64_t nb = bound_key(p.select_threshold + float(lvl) * kLevelStep - 2e-6f);
+                    if (nb > bound) bound = nb;
+                }
+                load_levels(it + 1, lv_lo, lv_hi);                             // prefetch for the next tile
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
             mbar_wait(tmem_full_bar(t), tph, p.status, 5);
             tc_fence_after();
 #pragma unroll 1
             for (int chunk = 0; chunk < kTileRows / 32; ++chunk) {
+                // segments [32*chunk, +32) of the tile: s_asr at column 128*(chunk/2) + 32*(chunk%2), s_audio 64 further
+                const uint32_t ta = lane_addr + t * 256u + uint32_t((chunk >> 1) * 128 + (chunk & 1) * 32);
                 uint32_t va[32], vb[32];
-                tc_ld32(lane_addr + t * 256u + uint32_t(chunk * 32), va);
-                tc_ld32(lane_addr + t * 256u + 128u + uint32_t(chunk * 32), vb);
+                tc_ld32(ta, va);
+                tc_ld32(ta + 64u, vb);
                 tc_wait_ld();
-                const uint32_t *fl4 = reinterpret_cast<const uint32_t *>(s_flags + t * kTileRows + chunk * 32);
+                const uint32_t col0 = row0 + uint32_t(chunk * 32);
+                const float bound_f = key_score(bound);
+                uint32_t m = 0;                                                // bit j: column j may enter the list
+                float f[32];
+                if (fast) {
+                    // branch-free: 4 independent instructions per score, full ILP across the 32 columns
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const uint32_t fl = (fl4[j >> 2] >> (8 * (j & 3))) & 0xFFu;
-                    const float fused = fuse32(__uint_as_float(va[j]), __uint_as_float(vb[j]), fl, w);
-                    const uint64_t key = make_key(fused, uint32_t(row0) + uint32_t(chunk * 32 + j));
-                    if (key > bound) list[cnt++] = key;
+                    for (int j = 0; j < 32; ++j) {
+                        f[j] = fmaf(w.wa, __uint_as_float(va[j]), w.wb * __uint_as_float(vb[j]));
+                        m |= f[j] >= bound_f ? (1u << j) : 0u;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const uint32_t wd = __shfl_sync(kFull, fw, (chunk * 32 + j) >> 2);
+                        f[j] = fuse32(__uint_as_float(va[j]), __uint_as_float(vb[j]), (wd >> (8 * (j & 3))) & 0xFFu, w);
+                        m |= f[j] >= bound_f ? (1u << j) : 0u;
+                    }
+                }
+                // Rare survivors.  The loop runs over the union of the lanes' masks, so the column index
+                // is warp-uniform and the register pair is picked by a jump table (no divergence, no
+                // TMEM re-read); only the lanes that flagged the column push.
+                uint32_t um = __reduce_or_sync(kFull, m);
+                while (um) {
+                    const int j = __ffs(um) - 1;
+                    um &= um - 1;
+                    float fj = 0.f;
+                    switch (j) {
+#define CAB_PICK(J) case J: fj = f[J]; break;
+                        CAB_PICK(0) CAB_PICK(1) CAB_PICK(2) CAB_PICK(3) CAB_PICK(4) CAB_PICK(5) CAB_PICK(6) CAB_PICK(7)
+                        CAB_PICK(8) CAB_PICK(9) CAB_PICK(10) CAB_PICK(11) CAB_PICK(12) CAB_PICK(13) CAB_PICK(14) CAB_PICK(15)
+                        CAB_PICK(16) CAB_PICK(17) CAB_PICK(18) CAB_PICK(19) CAB_PICK(20) CAB_PICK(21) CAB_PICK(22) CAB_PICK(23)
+                        CAB_PICK(24) CAB_PICK(25) CAB_PICK(26) CAB_PICK(27) CAB_PICK(28) CAB_PICK(29) CAB_PICK(30) CAB_PICK(31)
+#undef CAB_PICK
+                    }
+                    if ((m >> j) & 1u) push(fj, col0 + uint32_t(j));
                 }
                 // A list that could overflow during the next chunk is compacted by the whole warp.
                 unsigned need = __ballot_sync(kFull, cnt > kGemmListCap - 32);
@@ -335,8 +419,10 @@ gemm_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                     if (lane == src) { cnt = p.k; if (kth > bound) bound = kth; }
                 }
             }
+            // this warp's TMEM reads of stage t are complete: one arrive per warp on the leader's barrier
             tc_fence_before();
-            mbar_arrive_cluster(t == 0 ? tmem_empty_leader0 : tmem_empty_leader1);
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(t == 0 ? tmem_empty_leader0 : tmem_empty_leader1);
         }
         if (q < kGemmQueriesPerPass) p.counts[size_t(q) * p.n_pairs + pair] = q_valid ? cnt : 0;
     }
@@ -386,10 +472,11 @@ static bool make_map(CUtensorMap *m, const void *base, uint64_t rows, uint32_t b
 bool gemm_path_available() { return true; }
 int gemm_partials_per_query(int sm_count) { return sm_count / 2; }
 
-// workspace: [counts 256 x n_pairs int32][bf16 queries 256 x 384][status int]
+// workspace: [counts 256 x n_pairs int32][bf16 queries 256 x 384][levels 256 x 64 int32][status int]
 static size_t ws_counts_bytes(int sm_count) { return ((size_t(kGemmQueriesPerPass) * (sm_count / 2) * 4 + 255) / 256) * 256; }
 static size_t ws_queries_bytes() { return size_t(kGemmQueriesPerPass) * kDim * 2; }
-size_t gemm_workspace_bytes(int, int, int sm_count) { return ws_counts_bytes(sm_count) + ws_queries_bytes() + 256; }
+static size_t ws_levels_bytes() { return size_t(kGemmQueriesPerPass) * kLevels * 4; }
+size_t gemm_workspace_bytes(int, int, int sm_count) { return ws_counts_bytes(sm_count) + ws_queries_bytes() + ws_levels_bytes() + 256; }
 
 void launch_gemm_scan(const ScanArgs &a, int sm_count, void *workspace, size_t workspace_bytes,
                       cudaStream_t s, std::string *err) {
@@ -399,7 +486,8 @@ void launch_gemm_scan(const ScanArgs &a, int sm_count, void *workspace, size_t w
     uint8_t *ws = static_cast<uint8_t *>(workspace);
     int32_t *counts = reinterpret_cast<int32_t *>(ws);
     __nv_bfloat16 *qb = reinterpret_cast<__nv_bfloat16 *>(ws + ws_counts_bytes(sm_count));
-    int *status = reinterpret_cast<int *>(ws + ws_counts_bytes(sm_count) + ws_queries_bytes());
+    int32_t *levels = reinterpret_cast<int32_t *>(ws + ws_counts_bytes(sm_count) + ws_queries_bytes());
+    int *status = reinterpret_cast<int *>(ws + ws_counts_bytes(sm_count) + ws_queries_bytes() + ws_levels_bytes());
 
     static bool attr_done = false;
     if (!attr_done) {
@@ -412,13 +500,13 @@ void launch_gemm_scan(const ScanArgs &a, int sm_count, void *workspace, size_t w
     if (!make_map(&ma, a.asr, uint64_t(a.n_rows), kHalfRows, err)) return;
     if (!make_map(&mb, a.audio, uint64_t(a.n_rows), kHalfRows, err)) return;
 
-    cudaMemsetAsync(status, 0, sizeof(int), s);
+    cudaMemsetAsync(levels, 0, ws_levels_bytes() + sizeof(int), s);          // level histogram + status
     prep_queries_kernel<<<kGemmQueriesPerPass / 8, 256, 0, s>>>(a.queries, a.n_queries, qb, a.nonfinite);
 
     GemmParams p{};
     p.flags = a.flags; p.n_rows = a.n_rows; p.wa32 = a.wa32; p.wb32 = a.wb32; p.n_queries = a.n_queries;
     p.k = a.k; p.select_threshold = a.select_threshold; p.lists = a.partial_keys; p.counts = counts;
-    p.n_pairs = sm_count / 2; p.status = status;
+    p.n_pairs = sm_count / 2; p.status = status; p.levels = levels;
     gemm_scan_kernel<<<2 * p.n_pairs, kGemmThreads, kGemmSmemBytes, s>>>(mq, ma, mb, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) *err = std::string("gemm_scan_kernel launch: ") + cudaGetErrorString(e);
