@@ -192,7 +192,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from multimodal_audio_search_b200 import SegmentIndex, synth
+    from multimodal_audio_search_b200 import SegmentIndex, ShardedSearcher, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -220,23 +220,19 @@ def main():
     wa_all = np.array([w_classes[i % len(w_classes)] for i in range(n_steps * nq)])
     wb_all = 1.0 - wa_all
     q_dev = torch.from_numpy(q_host).cuda()
-    gathered = torch.empty((world, nq, k, 24), dtype=torch.uint8, device="cuda") if world > 1 else None
+    sharded = ShardedSearcher(idx, rank, world)
 
     def step_device(i):
         sl = slice(i * nq, (i + 1) * nq)
         if world == 1:
             return idx.search(q_dev[sl], wa_all[sl], wb_all[sl], k=k, path=path, threshold=args.threshold)
-        c = idx.search_candidates(q_dev[sl], wa_all[sl], wb_all[sl], k=k, path=path, threshold=args.threshold)
-        dist.all_gather_into_tensor(gathered, c)
-        return idx.merge_candidates(gathered, wa_all[sl], wb_all[sl], k=k, threshold=args.threshold, to_host=False)
+        return sharded.search(q_dev[sl], wa_all[sl], wb_all[sl], k=k, threshold=args.threshold, path=path, to_host=False)
 
     def step_host(i):
         sl = slice(i * nq, (i + 1) * nq)
         if world == 1:
             return idx.search(q_host[sl], wa_all[sl], wb_all[sl], k=k, path=path, threshold=args.threshold)
-        c = idx.search_candidates(q_host[sl], wa_all[sl], wb_all[sl], k=k, path=path, threshold=args.threshold)
-        dist.all_gather_into_tensor(gathered, c)
-        return idx.merge_candidates(gathered, wa_all[sl], wb_all[sl], k=k, threshold=args.threshold, to_host=True)
+        return sharded.search(q_host[sl], wa_all[sl], wb_all[sl], k=k, threshold=args.threshold, path=path, to_host=True)
 
     def barrier():
         if world > 1:

@@ -1,0 +1,54 @@
+"""Corpus sharded by segment over the GPUs of one box (one process per GPU, torch.distributed).
+
+Each rank owns the contiguous global segment range `shard_range(n_total, rank, world)` in its own
+`SegmentIndex` (with `row_base` = first global segment), so a search is:
+
+  1. local fused scan -> this shard's top-k as packed 24-byte candidates   (libcab, on device)
+  2. ONE all-gather of the candidate blocks  [world, Q, k, 24]            (NCCL over NVLink;
+     <= 24 B x k x Q per rank: latency-bound, it is the path's only exchange step)
+  3. merge on every rank: float64 reference fusion, threshold, (score desc, global index asc),
+     first k                                                              (libcab, on device)
+
+Queries and weights are replicated (1.5 KB per query).  The reference has no counterpart: it is a
+single-process loop over one Python list (audio_search.py:639).
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import numpy as np
+
+CANDIDATE_DTYPE = np.dtype([("index", "<i8"), ("asr_sim", "<f4"), ("audio_sim", "<f4"),
+                            ("flags", "<u4"), ("pad", "<u4")])      # cab_candidate, 24 bytes
+
+
+def shard_range(n_total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, near-equal split: rank r owns [r*ceil(n/world), ...) clipped to n_total."""
+    per = -(-n_total // world)
+    lo = min(n_total, rank * per)
+    return lo, min(n_total, lo + per)
+
+
+class ShardedSearcher:
+    """Drives steps 1-3 for one rank.  `index` is this rank's SegmentIndex (or any object with
+    `search_candidates` / `merge_candidates`); `group` a torch.distributed process group."""
+
+    def __init__(self, index, rank: int = 0, world: int = 1, group=None):
+        self.index, self.rank, self.world, self.group = index, rank, world, group
+        self._gathered = None
+
+    def search(self, queries, w_asr, w_audio, k: int = 10, threshold: float = 0.1, path: str = "auto",
+               to_host: bool = True):
+        import torch
+        import torch.distributed as dist
+        cands = self.index.search_candidates(queries, w_asr, w_audio, k=k, threshold=threshold, path=path)
+        if self.world == 1:
+            gathered = cands.unsqueeze(0)
+        else:
+            # concatenated layout [world*Q, k, 24] (accepted by both NCCL and gloo), viewed per rank
+            shape = (self.world * cands.shape[0],) + tuple(cands.shape[1:])
+            if self._gathered is None or tuple(self._gathered.shape) != shape or self._gathered.device != cands.device:
+                self._gathered = torch.empty(shape, dtype=cands.dtype, device=cands.device)
+            dist.all_gather_into_tensor(self._gathered, cands.contiguous(), group=self.group)
+            gathered = self._gathered.view((self.world,) + tuple(cands.shape))
+        return self.index.merge_candidates(gathered, w_asr, w_audio, k=k, threshold=threshold, to_host=to_host)
