@@ -138,6 +138,11 @@ def run_reference(args):
         return
     n_rows, dtype, nq, k, _ = WORKLOADS[args.workload]
     from oracle import numpy_oracle as no
+    try:        # torchrun exports OMP_NUM_THREADS=1; the CPU arm may use every host core
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
     rng = np.random.default_rng(1)
     sample = min(n_rows, 1_000_000)
     a = rng.standard_normal((sample, 384), dtype=np.float32)

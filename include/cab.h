@@ -127,7 +127,8 @@ CAB_API int cab_search(cab_index *idx, const float *queries, int queries_loc, co
 /* ---- sharded search (corpus split by segment over ranks) ----------------------------------
  * Step 1, per rank: local top-k as packed candidates (cab_candidate[n_queries x k], device).
  * Step 2, host plumbing: all-gather the candidate blocks of all ranks (NCCL over NVLink).
- * Step 3, per rank: merge world x k candidates per query into the final top-k. */
+ * Step 3, per rank: merge world x k candidates per query into the final top-k
+ *         (w_asr = w_audio = NULL reuses the weights staged by step 1 on the same handle). */
 typedef struct cab_candidate {
     int64_t index;       /* global segment index, -1 = empty slot */
     float asr_sim;

@@ -40,11 +40,13 @@ struct cab_index {
     uint8_t *d_params = nullptr;   size_t sz_params = 0;
     double *d_w64 = nullptr;       // views into d_params, set by stage_params
     float *d_w32 = nullptr;
+    int staged_nq = 0;             // number of queries whose weights are currently staged
     uint64_t *d_partial_keys = nullptr;  size_t sz_pkeys = 0;
     cab_candidate *d_cands = nullptr;    size_t sz_cands = 0;
     uint8_t *d_out = nullptr;      size_t d_out_bytes = 0;  // packed outputs
     uint8_t *d_gemm_ws = nullptr;  size_t d_gemm_ws_bytes = 0;
     int *d_nonfinite = nullptr;
+    unsigned int *d_counters = nullptr;     // [64] GEMV chunk tickets (zero between searches)
     // pinned host staging
     uint8_t *h_in = nullptr;  size_t h_in_bytes = 0;
     uint8_t *h_out = nullptr; size_t h_out_bytes = 0;
@@ -157,6 +159,8 @@ int cab_index_create(int dim, int dtype, int64_t capacity_rows, int device, cab_
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&idx->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&idx->d_nonfinite, sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(idx->d_nonfinite, 0, sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&idx->d_counters, 64 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(idx->d_counters, 0, 64 * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&idx->ev_in, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreate(&idx->ev_t0);
     if (e == cudaSuccess) e = cudaEventCreate(&idx->ev_t1);
@@ -180,7 +184,7 @@ int cab_index_destroy(cab_index *idx) {
     cudaFree(idx->asr); cudaFree(idx->audio); cudaFree(idx->flags);
     cudaFree(idx->d_params);
     cudaFree(idx->d_partial_keys); cudaFree(idx->d_cands);
-    cudaFree(idx->d_out); cudaFree(idx->d_gemm_ws); cudaFree(idx->d_nonfinite); cudaFree(idx->d_rows);
+    cudaFree(idx->d_out); cudaFree(idx->d_gemm_ws); cudaFree(idx->d_nonfinite); cudaFree(idx->d_rows); cudaFree(idx->d_counters);
     cudaFreeHost(idx->h_in); cudaFreeHost(idx->h_out); cudaFreeHost(idx->h_rows);
     if (idx->ev_in) cudaEventDestroy(idx->ev_in);
     if (idx->ev_t0) cudaEventDestroy(idx->ev_t0);
@@ -466,6 +470,7 @@ static int stage_params(cab_index *idx, const float *queries, int queries_loc, c
     idx->ev_in_pending = true;
     idx->d_w64 = reinterpret_cast<double *>(idx->d_params);
     idx->d_w32 = reinterpret_cast<float *>(idx->d_params + size_t(nq) * 16);
+    idx->staged_nq = nq;
     if (dq) *dq = qbytes ? reinterpret_cast<const float *>(idx->d_params + wbytes) : queries;
     return CAB_OK;
 }
@@ -477,7 +482,7 @@ struct UserOut {
 };
 static int run_local(cab_index *idx, const float *queries, int queries_loc, const double *w_asr,
                      const double *w_audio, int nq, int k, double threshold, int path,
-                     const UserOut *out, cudaStream_t s) {
+                     const UserOut *out, cab_candidate *cand_dst, cudaStream_t s) {
     if (!queries || !w_asr || !w_audio) return fail(idx, CAB_ERR_INVALID, "queries / weights are null");
     if (queries_loc != CAB_HOST && queries_loc != CAB_DEVICE) return fail(idx, CAB_ERR_INVALID, "queries_loc");
     if (nq <= 0 || nq > CAB_MAX_QUERIES) return fail(idx, CAB_ERR_INVALID, "n_queries must be in 1..%d", CAB_MAX_QUERIES);
@@ -510,10 +515,11 @@ static int run_local(cab_index *idx, const float *queries, int queries_loc, cons
     if (out) ea = make_emit(idx, 1, nq, k, threshold, out->index, out->fusion, out->asr, out->audio,
                             out->flags, out->count, out->loc);
     idx->timed = false;
+    cab_candidate *cands = cand_dst ? cand_dst : idx->d_cands;      // sharded search: straight into the caller's block
     if (idx->size == 0) {
         // nothing to scan: every candidate slot is empty
-        CU(idx, cudaMemsetAsync(idx->d_cands, 0xFF, size_t(nq) * k * sizeof(cab_candidate), s));
-        if (out) { ea.cands = idx->d_cands; launch_emit(ea, s); idx->launches += 1; CU(idx, cudaGetLastError()); }
+        CU(idx, cudaMemsetAsync(cands, 0xFF, size_t(nq) * k * sizeof(cab_candidate), s));
+        if (out) { ea.cands = cands; launch_emit(ea, s); idx->launches += 1; CU(idx, cudaGetLastError()); }
         return CAB_OK;
     }
 
@@ -522,12 +528,13 @@ static int run_local(cab_index *idx, const float *queries, int queries_loc, cons
     sa.dtype = idx->dtype; sa.k = k;
     sa.select_threshold = float(threshold) - 1e-6f;
     sa.partial_keys = idx->d_partial_keys;
-    sa.n_partials = n_partials; sa.nonfinite = idx->d_nonfinite;
+    sa.n_partials = n_partials; sa.nonfinite = idx->d_nonfinite; sa.work_counters = idx->d_counters;
     FinalizeArgs fa{};
     fa.asr = idx->asr; fa.audio = idx->audio; fa.flags = idx->flags; fa.dtype = idx->dtype;
     fa.row_base = idx->row_base; fa.k = k; fa.partial_keys = idx->d_partial_keys;
     fa.n_partials = n_partials; fa.force_general = int(idx->opt_finalize_general);
     fa.slot_stride = use_gemm ? kGemmListCap : k;
+    fa.work_counters = use_gemm ? nullptr : idx->d_counters;
     fa.counts = use_gemm ? reinterpret_cast<const int32_t *>(idx->d_gemm_ws) : nullptr;
 
     if (idx->opt_time_kernels) CU(idx, cudaEventRecord(idx->ev_t0, s));
@@ -543,7 +550,7 @@ static int run_local(cab_index *idx, const float *queries, int queries_loc, cons
             launch_gemv_scan(sa, idx->gemv, idx->sm_count, s);
         }
         if (idx->opt_time_kernels && q0 + batch >= nq) CU(idx, cudaEventRecord(idx->ev_t1, s));
-        fa.queries = sa.queries; fa.n_queries = m; fa.cands = idx->d_cands + size_t(q0) * k;
+        fa.queries = sa.queries; fa.n_queries = m; fa.cands = cands + size_t(q0) * k;
         if (out) {
             EmitArgs eb = ea;                           // this batch's slice of the outputs
             eb.n_queries = m;
@@ -598,7 +605,7 @@ int cab_search(cab_index *idx, const float *queries, int queries_loc, const doub
     CHECK_HANDLE(idx);
     cudaStream_t s = stream ? (cudaStream_t)stream : idx->own_stream;
     const UserOut o{out_index, out_fusion, out_asr, out_audio, out_flags, out_count, out_loc};
-    int rc = run_local(idx, queries, queries_loc, w_asr, w_audio, n_queries, k, threshold, path, &o, s);
+    int rc = run_local(idx, queries, queries_loc, w_asr, w_audio, n_queries, k, threshold, path, &o, nullptr, s);
     if (rc != CAB_OK) return rc;
     return finish_outputs(idx, n_queries, k, o, s);
 }
@@ -609,10 +616,8 @@ int cab_search_candidates(cab_index *idx, const float *queries, int queries_loc,
     CHECK_HANDLE(idx);
     if (!out_device) return fail(idx, CAB_ERR_INVALID, "out_device is null");
     cudaStream_t s = stream ? (cudaStream_t)stream : idx->own_stream;
-    int rc = run_local(idx, queries, queries_loc, w_asr, w_audio, n_queries, k, threshold, path, nullptr, s);
+    int rc = run_local(idx, queries, queries_loc, w_asr, w_audio, n_queries, k, threshold, path, nullptr, out_device, s);
     if (rc != CAB_OK) return rc;
-    CU(idx, cudaMemcpyAsync(out_device, idx->d_cands, size_t(n_queries) * k * sizeof(cab_candidate),
-                            cudaMemcpyDeviceToDevice, s));
     if (idx->opt_sync) CU(idx, cudaStreamSynchronize(s));
     return CAB_OK;
 }
@@ -623,7 +628,9 @@ int cab_merge_candidates(cab_index *idx, const cab_candidate *cands_device, int 
                          float *out_audio, uint8_t *out_flags, int32_t *out_count, int out_loc,
                          void *stream) {
     CHECK_HANDLE(idx);
-    if (!cands_device || !w_asr || !w_audio || n_lists <= 0) return fail(idx, CAB_ERR_INVALID, "bad merge arguments");
+    if (!cands_device || n_lists <= 0 || (!w_asr) != (!w_audio)) return fail(idx, CAB_ERR_INVALID, "bad merge arguments");
+    // w_asr == w_audio == NULL: reuse the weights staged by the preceding cab_search_candidates
+    if (!w_asr && idx->staged_nq != n_queries) return fail(idx, CAB_ERR_INVALID, "no staged weights for %d queries", n_queries);
     if (n_queries <= 0 || n_queries > CAB_MAX_QUERIES || k <= 0 || k > CAB_MAX_K) return fail(idx, CAB_ERR_INVALID, "bad n_queries / k");
     if (size_t(n_lists) * k > 1024) return fail(idx, CAB_ERR_INVALID, "n_lists * k must be <= 1024");
     if (out_loc != CAB_HOST && out_loc != CAB_DEVICE) return fail(idx, CAB_ERR_INVALID, "out_loc");
@@ -631,7 +638,7 @@ int cab_merge_candidates(cab_index *idx, const cab_candidate *cands_device, int 
     cudaStream_t s = stream ? (cudaStream_t)stream : idx->own_stream;
     int rc = ensure_workspace(idx, n_queries, k, 1, 1, k, 0);
     if (rc != CAB_OK) return rc;
-    if ((rc = stage_params(idx, nullptr, CAB_DEVICE, w_asr, w_audio, n_queries, s, nullptr))) return rc;
+    if (w_asr && (rc = stage_params(idx, nullptr, CAB_DEVICE, w_asr, w_audio, n_queries, s, nullptr))) return rc;
     const UserOut o{out_index, out_fusion, out_asr, out_audio, out_flags, out_count, out_loc};
     EmitArgs ea = make_emit(idx, n_lists, n_queries, k, threshold, out_index, out_fusion, out_asr,
                             out_audio, out_flags, out_count, out_loc);

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, E
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int qi = blockIdx.x;
-    if (threadIdx.x == 0) { s_cnt = 0; s_bound = 0ull; }
+    if (threadIdx.x == 0) { s_cnt = 0; s_bound = 0ull; if (a.work_counters) a.work_counters[qi] = 0u; }
     __syncthreads();
 
     // Sort the buffer, keep the best k, raise the bound.  Block-uniform.

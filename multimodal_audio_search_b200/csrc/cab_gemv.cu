@@ -67,9 +67,23 @@ gemv_scan_kernel(ScanArgs a) {
     const uint4 *__restrict__ B = reinterpret_cast<const uint4 *>(a.audio);
     const int64_t n = a.n_rows;
     const int64_t gwarp = int64_t(blockIdx.x) * kScanWarps + warp;
-    const int64_t step = int64_t(gridDim.x) * kScanWarps * kRowsPerIter;
+    const int64_t total_warps = int64_t(gridDim.x) * kScanWarps;
 
-    for (int64_t base = gwarp * kRowsPerIter; base < n; base += step) {
+    // Dynamic chunk scheduling: a warp's first chunk is static (its global warp id); every further
+    // chunk comes from a per-query atomic counter, fetched one chunk ahead so the atomic's latency
+    // is hidden.  Unlike a static split this tolerates SMs that are late or busy (another kernel,
+    // e.g. an NCCL collective, holding an SM) and evens out SM-to-SM speed differences.
+    constexpr int kChunkRows = kRowsPerIter * (64 / kRowsPerIter);      // 64 rows per chunk
+    const int64_t n_chunks = (n + kChunkRows - 1) / kChunkRows;
+    unsigned int *counter = a.work_counters + qi;
+    int64_t chunk = gwarp;
+    unsigned int ticket = 0;                                  // lane 0: result of the in-flight atomic
+    if (chunk < n_chunks && lane == 0) ticket = atomicAdd(counter, 1u);
+
+    for (; chunk < n_chunks;
+         chunk = total_warps + int64_t(__shfl_sync(kFull, ticket, 0)),
+         ticket = (lane == 0 && chunk < n_chunks) ? atomicAdd(counter, 1u) : 0u)
+    for (int64_t base = chunk * kChunkRows, cend = base + kChunkRows; base < cend && base < n; base += kRowsPerIter) {
         uint4 ca[U][3], cb[U][3];
 #pragma unroll
         for (int u = 0; u < U; ++u) {

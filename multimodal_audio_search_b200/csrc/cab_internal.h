@@ -46,6 +46,7 @@ struct ScanArgs {
     int32_t *partial_counts;   // GEMM only: [n_queries][n_partials]
     int n_partials;            // == grid size of the scan (GEMV) / number of CTA pairs (GEMM)
     int *nonfinite;            // set if a query holds NaN/Inf
+    unsigned int *work_counters;   // GEMV: [n_queries] chunk tickets, zero on entry (finalize resets them)
 };
 struct GemvConfig {
     int variant;               // 0 = LDG register pipeline, 1 = bulk-copy smem ring
@@ -80,6 +81,7 @@ struct FinalizeArgs {
     int slot_stride;
     cab_candidate *cands;      // out [n_queries][k], best-first by scan score, index -1 = empty
     int force_general;         // test hook: skip the head-bound fast path
+    unsigned int *work_counters;   // [n_queries] reset to 0 for the next scan (may be null)
 };
 struct EmitArgs;
 // fused_emit != nullptr (single candidate list): the emit stage runs inside the same kernel.

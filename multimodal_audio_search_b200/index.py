@@ -219,12 +219,13 @@ class SegmentIndex:
 
     def merge_candidates(self, gathered, w_asr=0.5, w_audio=0.5, k: int = 10,
                          threshold: float = 0.1, to_host: bool = True) -> SearchResult:
-        """Merge candidate blocks of all shards: CUDA uint8 [world, Q, k, 24] -> final top-k."""
+        """Merge candidate blocks of all shards: CUDA uint8 [world, Q, k, 24] -> final top-k.
+        w_asr = w_audio = None reuses the weights staged by the preceding search_candidates."""
         import torch
         world, nq = gathered.shape[0], gathered.shape[1]
         if gathered.shape[2] != k or gathered.shape[3] != N.CANDIDATE_BYTES or not gathered.is_contiguous():
             raise ValueError("gathered must be contiguous uint8 [world, Q, k, 24]")
-        wa, wb = self._weights(w_asr, w_audio, nq)
+        wa, wb = (None, None) if w_asr is None else self._weights(w_asr, w_audio, nq)
         if to_host:
             out = SearchResult(np.empty((nq, k), np.int64), np.empty((nq, k), np.float64),
                                np.empty((nq, k), np.float32), np.empty((nq, k), np.float32),

@@ -51,4 +51,5 @@ class ShardedSearcher:
                 self._gathered = torch.empty(shape, dtype=cands.dtype, device=cands.device)
             dist.all_gather_into_tensor(self._gathered, cands.contiguous(), group=self.group)
             gathered = self._gathered.view((self.world,) + tuple(cands.shape))
-        return self.index.merge_candidates(gathered, w_asr, w_audio, k=k, threshold=threshold, to_host=to_host)
+        # the weights are already on the device (staged by search_candidates on the same handle)
+        return self.index.merge_candidates(gathered, None, None, k=k, threshold=threshold, to_host=to_host)

@@ -30,6 +30,7 @@ class FakeShardIndex:
 
     def search_candidates(self, queries, w_asr, w_audio, k, threshold, path):
         import torch
+        self._w = (w_asr, w_audio)
         out = np.zeros((len(queries), k), dtype=CANDIDATE_DTYPE)
         out["index"] = -1
         for i, q in enumerate(queries):
@@ -42,6 +43,7 @@ class FakeShardIndex:
         return torch.from_numpy(out.view(np.uint8).reshape(len(queries), k, 24))
 
     def merge_candidates(self, gathered, w_asr, w_audio, k, threshold, to_host):
+        w_asr, w_audio = self._w          # reuse the weights of the preceding search_candidates
         c = gathered.numpy().reshape(gathered.shape[0], gathered.shape[1], k * 24).view(CANDIDATE_DTYPE)
         res = []
         for i in range(c.shape[1]):
