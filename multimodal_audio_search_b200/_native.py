@@ -94,6 +94,24 @@ def lib() -> C.CDLL:
     return handle
 
 
+TORCH_LIB_PATH = os.path.join(HERE, "libcab_torch.so")
+_torch_ops = None
+
+
+def torch_ops():
+    """`torch.ops.cab` from the PyTorch extension (libcab_torch.so), loaded once."""
+    global _torch_ops
+    if _torch_ops is None:
+        lib()                                   # libcab.so first (the extension links it)
+        if not os.path.exists(TORCH_LIB_PATH):
+            raise NativeLibraryMissing(
+                f"{TORCH_LIB_PATH} not found: build it with `python -m multimodal_audio_search_b200.build`")
+        import torch
+        torch.ops.load_library(TORCH_LIB_PATH)
+        _torch_ops = torch.ops.cab
+    return _torch_ops
+
+
 def check(status: int, handle=None):
     if status == CAB_OK:
         return

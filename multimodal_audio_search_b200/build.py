@@ -18,6 +18,8 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libcab.so")
+TORCH_LIB = os.path.join(HERE, "libcab_torch.so")
+TORCH_SRC = os.path.join(CSRC, "torch_binding.cpp")
 
 SOURCES = ["cab_api.cu", "cab_ingest.cu", "cab_gemv.cu", "cab_finalize.cu",
            "cab_gemm_tc.cu"]
@@ -77,5 +79,28 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_torch_extension(force: bool = False) -> str:
+    """PyTorch extension over the C-ABI (csrc/torch_binding.cpp -> libcab_torch.so): registers
+    torch.ops.cab.*; links libcab.so via $ORIGIN.  Plain g++ against the installed torch headers."""
+    import torch
+    from torch.utils import cpp_extension as ce
+    newest = max(os.path.getmtime(TORCH_SRC), os.path.getmtime(os.path.join(INCLUDE, "cab.h")), os.path.getmtime(LIB))
+    if not force and os.path.exists(TORCH_LIB) and os.path.getmtime(TORCH_LIB) >= newest:
+        return TORCH_LIB
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC",
+           f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}", TORCH_SRC, "-o", TORCH_LIB]
+    for inc in ce.include_paths() + [cuda_inc]:
+        cmd += ["-isystem", inc]
+    for lp in ce.library_paths():
+        cmd += [f"-L{lp}", f"-Wl,-rpath,{lp}"]
+    cmd += [f"-L{HERE}", "-Wl,-rpath,$ORIGIN", "-lcab", "-ltorch", "-ltorch_cpu", "-lc10", "-lc10_cuda", "-ltorch_cuda"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"torch extension build failed:\n{r.stdout}\n{r.stderr}")
+    return TORCH_LIB
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build_torch_extension(force="--force" in sys.argv))

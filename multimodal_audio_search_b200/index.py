@@ -122,10 +122,7 @@ class SegmentIndex:
                 f = flags if _is_torch_cuda(flags) else torch.as_tensor(np.asarray(flags, np.uint8)).cuda(self.device)
                 if f.dtype != torch.uint8 or f.numel() != n:
                     raise ValueError("flags must be uint8 [n]")
-            N.check(self._lib.cab_index_append(
-                self._h, None if asr_rows is None else C.c_void_p(asr_rows.data_ptr()),
-                None if audio_rows is None else C.c_void_p(audio_rows.data_ptr()),
-                None if f is None else C.c_void_p(f.data_ptr()), n, N.CAB_DEVICE, self._stream()), self._h)
+            N.torch_ops().append(self._h.value, asr_rows, audio_rows, f)
             return
         a = None if asr_rows is None else _np_f32(asr_rows, self.dim)
         b = None if audio_rows is None else _np_f32(audio_rows, self.dim)
@@ -179,25 +176,13 @@ class SegmentIndex:
         return out
 
     def _search_device(self, queries, w_asr, w_audio, k, threshold, path) -> SearchResult:
+        """CUDA tensors in, CUDA tensors out, through the PyTorch extension (torch.ops.cab.search)."""
         import torch
         q = queries if queries.dim() == 2 else queries.unsqueeze(0)
-        if q.dtype != torch.float32 or q.shape[1] != self.dim or not q.is_contiguous():
-            raise ValueError("device queries must be contiguous float32 [Q x 384]")
-        nq = q.shape[0]
-        wa, wb = self._weights(w_asr, w_audio, nq)
-        dev = q.device
-        out = SearchResult(torch.empty((nq, k), dtype=torch.int64, device=dev),
-                           torch.empty((nq, k), dtype=torch.float64, device=dev),
-                           torch.empty((nq, k), dtype=torch.float32, device=dev),
-                           torch.empty((nq, k), dtype=torch.float32, device=dev),
-                           torch.empty((nq, k), dtype=torch.uint8, device=dev),
-                           torch.empty((nq,), dtype=torch.int32, device=dev))
-        p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
-        N.check(self._lib.cab_search(self._h, p(q), N.CAB_DEVICE, _ptr(wa), _ptr(wb), nq, k,
-                                     float(threshold), _PATHS[path], p(out.indices), p(out.fusion),
-                                     p(out.asr_sim), p(out.audio_sim), p(out.flags), p(out.count),
-                                     N.CAB_DEVICE, self._stream()), self._h)
-        return out
+        wa, wb = self._weights(w_asr, w_audio, q.shape[0])
+        out = N.torch_ops().search(self._h.value, q, torch.from_numpy(wa), torch.from_numpy(wb), int(k),
+                                   float(threshold), _PATHS[path])
+        return SearchResult(*out)
 
     # -- sharded search (corpus split by segment over ranks) -----------------------------------
     def search_candidates(self, queries, w_asr=0.5, w_audio=0.5, k: int = 10,
@@ -206,10 +191,11 @@ class SegmentIndex:
         import torch
         if _is_torch_cuda(queries):
             q = queries if queries.dim() == 2 else queries.unsqueeze(0)
-            qp, loc, nq = C.c_void_p(q.data_ptr()), N.CAB_DEVICE, q.shape[0]
-        else:
-            q = _np_f32(np.atleast_2d(queries), self.dim)
-            qp, loc, nq = _ptr(q), N.CAB_HOST, q.shape[0]
+            wa, wb = self._weights(w_asr, w_audio, q.shape[0])
+            return N.torch_ops().search_candidates(self._h.value, q, torch.from_numpy(wa), torch.from_numpy(wb),
+                                                   int(k), float(threshold), _PATHS[path])
+        q = _np_f32(np.atleast_2d(queries), self.dim)
+        qp, loc, nq = _ptr(q), N.CAB_HOST, q.shape[0]
         wa, wb = self._weights(w_asr, w_audio, nq)
         out = torch.empty((nq, k, N.CANDIDATE_BYTES), dtype=torch.uint8, device=f"cuda:{self.device}")
         N.check(self._lib.cab_search_candidates(self._h, qp, loc, _ptr(wa), _ptr(wb), nq, k,

@@ -62,3 +62,17 @@ def test_no_cpu_fallback(lib):
                                "asr_success": True, "audio_success": False})
     with pytest.raises(N.CabError):
         eng.search_with_fusion("anything")
+
+
+def test_torch_extension_registers_ops(lib):
+    """The PyTorch extension (libcab_torch.so) builds against the installed torch and registers
+    torch.ops.cab.* (no compute without a GPU)."""
+    from multimodal_audio_search_b200 import build
+    build.build_torch_extension()
+    ops = N.torch_ops()
+    for name in ("append", "search", "search_candidates", "merge_candidates"):
+        assert hasattr(ops, name)
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(Exception):      # CPU tensors are rejected, nothing is computed on the host
+            ops.search(0, torch.zeros(1, 384), torch.ones(1), torch.ones(1), 10, 0.1, 0)
