@@ -14,7 +14,8 @@
  *   - cab_last_error(idx) returns a static/handle-owned message for the last failure;
  *   - a handle is externally synchronised (one caller at a time); distinct handles may be used
  *     from distinct threads (the reference keeps one engine per Streamlit session, :708-711);
- *   - `stream` is a cudaStream_t passed as void* (NULL = the handle's own stream);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the handle's own non-blocking stream;
+ *     to run on the default stream pass cudaStreamLegacy / cudaStreamPerThread explicitly);
  *   - `*_loc` says where a caller buffer lives: CAB_HOST or CAB_DEVICE;
  *   - there is NO CPU fallback: without a usable CUDA device every call fails with
  *     CAB_ERR_NO_DEVICE.

@@ -15,6 +15,14 @@ namespace {
 
 cab_index *handle_of(int64_t h) { return reinterpret_cast<cab_index *>(static_cast<intptr_t>(h)); }
 
+// torch's current stream as the C-ABI wants it.  The C-ABI reads NULL as "the handle's own stream",
+// but torch's default stream IS the NULL handle: name it explicitly so the work is ordered with
+// the caller's stream.
+cudaStream_t current_stream() {
+    cudaStream_t s = current_stream();
+    return s ? s : cudaStreamLegacy;
+}
+
 void check(int status, cab_index *idx) {
     if (status == CAB_OK) return;
     const char *msg = cab_last_error(idx);
@@ -46,7 +54,7 @@ void append(int64_t h, const c10::optional<at::Tensor> &asr, const c10::optional
         TORCH_CHECK(flags->is_cuda() && flags->scalar_type() == at::kByte && flags->numel() == n && flags->is_contiguous(),
                     "flags must be a contiguous CUDA uint8 [n] tensor");
     c10::cuda::CUDAGuard guard(first.device());
-    cudaStream_t s = at::cuda::getCurrentCUDAStream();
+    cudaStream_t s = current_stream();
     check(cab_index_append(handle_of(h), asr.has_value() ? asr->data_ptr<float>() : nullptr,
                            audio.has_value() ? audio->data_ptr<float>() : nullptr,
                            flags.has_value() ? flags->data_ptr<uint8_t>() : nullptr, n, CAB_DEVICE, s),
@@ -64,7 +72,7 @@ search(int64_t h, const at::Tensor &queries, const at::Tensor &w_asr, const at::
     at::Tensor oi = at::empty({nq, k}, opt.dtype(at::kLong)), of = at::empty({nq, k}, opt.dtype(at::kDouble));
     at::Tensor oa = at::empty({nq, k}, opt.dtype(at::kFloat)), ob = at::empty({nq, k}, opt.dtype(at::kFloat));
     at::Tensor ofl = at::empty({nq, k}, opt.dtype(at::kByte)), oc = at::empty({nq}, opt.dtype(at::kInt));
-    cudaStream_t s = at::cuda::getCurrentCUDAStream();
+    cudaStream_t s = current_stream();
     check(cab_search(handle_of(h), queries.data_ptr<float>(), CAB_DEVICE, wa.data(), wb.data(), int(nq), int(k),
                      threshold, int(path), oi.data_ptr<int64_t>(), of.data_ptr<double>(), oa.data_ptr<float>(),
                      ob.data_ptr<float>(), ofl.data_ptr<uint8_t>(), oc.data_ptr<int32_t>(), CAB_DEVICE, s),
@@ -79,7 +87,7 @@ at::Tensor search_candidates(int64_t h, const at::Tensor &queries, const at::Ten
     const auto wa = host_weights(w_asr, nq, "w_asr"), wb = host_weights(w_audio, nq, "w_audio");
     c10::cuda::CUDAGuard guard(queries.device());
     at::Tensor out = at::empty({nq, k, int64_t(sizeof(cab_candidate))}, queries.options().dtype(at::kByte));
-    cudaStream_t s = at::cuda::getCurrentCUDAStream();
+    cudaStream_t s = current_stream();
     check(cab_search_candidates(handle_of(h), queries.data_ptr<float>(), CAB_DEVICE, wa.data(), wb.data(), int(nq),
                                 int(k), threshold, int(path), reinterpret_cast<cab_candidate *>(out.data_ptr<uint8_t>()), s),
           handle_of(h));
@@ -99,7 +107,7 @@ merge_candidates(int64_t h, const at::Tensor &gathered, const at::Tensor &w_asr,
     at::Tensor oi = at::empty({nq, k}, opt.dtype(at::kLong)), of = at::empty({nq, k}, opt.dtype(at::kDouble));
     at::Tensor oa = at::empty({nq, k}, opt.dtype(at::kFloat)), ob = at::empty({nq, k}, opt.dtype(at::kFloat));
     at::Tensor ofl = at::empty({nq, k}, opt.dtype(at::kByte)), oc = at::empty({nq}, opt.dtype(at::kInt));
-    cudaStream_t s = at::cuda::getCurrentCUDAStream();
+    cudaStream_t s = current_stream();
     check(cab_merge_candidates(handle_of(h), reinterpret_cast<const cab_candidate *>(gathered.data_ptr<uint8_t>()),
                                int(world), int(nq), int(k), wa.data(), wb.data(), threshold, oi.data_ptr<int64_t>(),
                                of.data_ptr<double>(), oa.data_ptr<float>(), ob.data_ptr<float>(),

@@ -102,8 +102,10 @@ class SegmentIndex:
         return float(self._lib.cab_index_last_scan_ms(self._h))
 
     def _stream(self):
+        """torch's current stream for the C-ABI.  NULL means "the handle's own stream" there, and
+        torch's default stream IS the NULL handle, so it is passed as cudaStreamLegacy (0x1)."""
         import torch
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream or 1)
 
     # -- ingest --------------------------------------------------------------------------------
     def append(self, asr_rows, audio_rows, flags=None):
@@ -153,8 +155,8 @@ class SegmentIndex:
     # -- search --------------------------------------------------------------------------------
     @staticmethod
     def _weights(w_asr, w_audio, nq):
-        wa = np.ascontiguousarray(np.broadcast_to(np.asarray(w_asr, dtype=np.float64), (nq,)))
-        wb = np.ascontiguousarray(np.broadcast_to(np.asarray(w_audio, dtype=np.float64), (nq,)))
+        wa = np.array(np.broadcast_to(np.asarray(w_asr, dtype=np.float64), (nq,)), dtype=np.float64)   # owned copies
+        wb = np.array(np.broadcast_to(np.asarray(w_audio, dtype=np.float64), (nq,)), dtype=np.float64)
         return wa, wb
 
     def search(self, queries, w_asr=0.5, w_audio=0.5, k: int = 10, threshold: float = 0.1,

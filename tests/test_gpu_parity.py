@@ -200,7 +200,7 @@ def test_device_tensor_interface():
     q = synth.raw_queries(seed, 0, 3)
     host = idx.search(q, [0.5, 0.2, 0.8], [0.5, 0.8, 0.2], k=20)
     dev = idx.search(torch.from_numpy(q).cuda(), [0.5, 0.2, 0.8], [0.5, 0.8, 0.2], k=20)
-    torch.cuda.synchronize()
+    # no device-wide synchronize: .cpu() must be ordered after the search on torch's current stream
     np.testing.assert_array_equal(dev.indices.cpu().numpy(), host.indices)
     np.testing.assert_array_equal(dev.fusion.cpu().numpy(), host.fusion)
     np.testing.assert_array_equal(dev.count.cpu().numpy(), host.count)
@@ -210,6 +210,28 @@ def test_device_tensor_interface():
     idx2.append(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), torch.from_numpy(f).cuda())
     host2 = idx2.search(q, [0.5, 0.2, 0.8], [0.5, 0.8, 0.2], k=20)
     np.testing.assert_array_equal(host2.indices, host.indices)
+
+
+def test_device_calls_are_ordered_on_the_callers_stream():
+    """Results of CUDA-tensor calls must be valid for stream-ordered consumers (no device sync),
+    on torch's default stream and on a side stream, for a scan long enough to expose a race."""
+    torch = pytest.importorskip("torch")
+    seed, n, nq = 8, 2_000_000, 512
+    idx = SegmentIndex("bf16", capacity=n)
+    idx.append_synth(seed, n, 0, n, n_queries=nq, plants=20)
+    q = synth.raw_queries(seed, 0, nq)
+    wa = np.full(nq, 0.4); wb = 1.0 - wa
+    host = idx.search(q, wa, wb, k=10, path="gemm")
+    qd = torch.from_numpy(q).cuda()
+    dev = idx.search(qd, wa, wb, k=10, path="gemm")
+    np.testing.assert_array_equal(dev.count.cpu().numpy(), host.count)
+    np.testing.assert_array_equal(dev.indices.cpu().numpy(), host.indices)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        dev2 = idx.search(qd[:40], wa[:40], wb[:40], k=10, path="gemv")
+        got = dev2.indices.cpu().numpy()
+    np.testing.assert_array_equal(got, host.indices[:40])
 
 
 def test_sharded_merge_equals_single_index():
