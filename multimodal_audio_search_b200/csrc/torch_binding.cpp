@@ -19,7 +19,7 @@ cab_index *handle_of(int64_t h) { return reinterpret_cast<cab_index *>(static_ca
 // but torch's default stream IS the NULL handle: name it explicitly so the work is ordered with
 // the caller's stream.
 cudaStream_t current_stream() {
-    cudaStream_t s = current_stream();
+    cudaStream_t s = at::cuda::getCurrentCUDAStream();
     return s ? s : cudaStreamLegacy;
 }
 
