@@ -91,11 +91,13 @@ class ClockSampler:
 
 
 def peaks():
+    """(HBM GB/s, bf16 TFLOP/s burst, bf16 TFLOP/s sustained, source)."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return d["hbm_gbs"], d.get("bf16_tflops", 1590.0), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+        return (d["hbm_gbs"], d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0),
+                "measured (MEASURED_PEAKS.json)")
+    return 6650.0, 1590.0, 1400.0, "fallback (B200_PROFILING.md)"
 
 
 def cpu_baseline(n_rows, dtype, k, max_seconds=25.0):
@@ -291,7 +293,7 @@ def main():
     scan_ms = max_over_ranks(scan_ms)
 
     if rank == 0:
-        hbm_peak, tc_peak, peak_src = peaks()
+        hbm_peak, tc_burst, tc_sustained, peak_src = peaks()
         norm = n_total / 1e6
         value = nq * 1e3 / ms_step * norm
         e2e_value = args.steps * nq / e2e_s * norm
@@ -299,9 +301,13 @@ def main():
         if path == "gemm":
             flops = nq * n_rows * 4 * 384
             achieved = flops / (scan_ms * 1e-3) / 1e12
-            roof = {"bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
-                    "frac": achieved / tc_peak, "traffic": None, "peak_source": peak_src,
-                    "hbm_gbs": alg_bytes / (scan_ms * 1e-3) / 1e9}
+            # back-to-back tensor-core steps run under the 1 kW power cap: the sustained cuBLAS figure is
+            # the matching denominator (B200_PROFILING.md); the burst fraction is reported beside it.
+            roof = {"bound": "tensor", "achieved": achieved, "peak": tc_sustained, "unit": "TFLOP/s",
+                    "frac": achieved / tc_sustained, "peak_kind": "sustained cuBLAS bf16 (kernel timed inside a long step)",
+                    "frac_of_burst_peak": achieved / tc_burst, "frac_of_2250_nominal": achieved / 2250.0,
+                    "traffic": None, "peak_source": peak_src, "kernel": "gemm_scan_kernel", "kernel_ms": scan_ms,
+                    "algorithmic_flops_per_launch": flops, "hbm_gbs": alg_bytes / (scan_ms * 1e-3) / 1e9}
         else:
             achieved = alg_bytes * nq / (scan_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",

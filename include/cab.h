@@ -108,6 +108,20 @@ CAB_API int cab_synth_queries(int device, uint32_t seed, int q0, int q1, float *
 CAB_API int cab_index_read_rows(cab_index *idx, int corpus /*0 asr, 1 audio*/, int64_t r0, int64_t r1,
                         float *out, int out_loc);
 
+/* ---- persistent index file (the reference keeps its library only
+ * in the Streamlit session, audio_search.py:708-711, and loses it when the session ends) ---------
+ * Layout (little endian): 4096-byte header {magic "CABIDX01", version, dim, dtype, n_rows,
+ * row_base, section offsets}, then the ASR rows, the audio rows (exactly as resident in HBM:
+ * L2-normalised fp32/bf16, row-major) and the flag bytes, each section 4096-byte aligned so the
+ * file can be mmap-ed.  A reload is bit-identical: rows are not re-normalised.  Segment metadata
+ * (texts, times, audio) stays with the caller. */
+CAB_API int cab_index_save(cab_index *idx, const char *path);
+/* Load rows [r0, r1) of a file into a new index on `device` (r1 < 0: to the end).  The new
+ * index's row_base is the file's row_base + r0, so shards of one file merge correctly. */
+CAB_API int cab_index_load(const char *path, int device, int64_t r0, int64_t r1, cab_index **out);
+/* Header fields without touching CUDA (any may be NULL). */
+CAB_API int cab_index_file_info(const char *path, int *dim, int *dtype, int64_t *n_rows, int64_t *row_base);
+
 /* ---- search: replaces the per-segment loop, threshold, sort and [:k]  (:639-685, :699) -------
  * queries : fp32 [n_queries x dim], raw (re-normalised like normalize(X) at :646);
  * w_asr, w_audio : host arrays [n_queries] of the query weights from

@@ -55,6 +55,9 @@ SIGNATURES = {
     "cab_index_append_synth": (_i32, [_p, _u32, _i64, _i64, _i64, _i32, _i32, _i32, _p]),
     "cab_synth_queries": (_i32, [_i32, _u32, _i32, _i32, _p, _i32]),
     "cab_index_read_rows": (_i32, [_p, _i32, _i64, _i64, _p, _i32]),
+    "cab_index_save": (_i32, [_p, C.c_char_p]),
+    "cab_index_load": (_i32, [C.c_char_p, _i32, _i64, _i64, C.POINTER(_p)]),
+    "cab_index_file_info": (_i32, [C.c_char_p, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i64), C.POINTER(_i64)]),
     "cab_search": (_i32, [_p, _p, _i32, _p, _p, _i32, _i32, _dbl, _i32, _p, _p, _p, _p, _p, _p, _i32, _p]),
     "cab_search_candidates": (_i32, [_p, _p, _i32, _p, _p, _i32, _i32, _dbl, _i32, _p, _p]),
     "cab_merge_candidates": (_i32, [_p, _p, _i32, _i32, _i32, _p, _p, _dbl, _p, _p, _p, _p, _p, _p, _i32, _p]),

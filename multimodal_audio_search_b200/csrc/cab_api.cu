@@ -389,6 +389,131 @@ int cab_index_read_rows(cab_index *idx, int corpus, int64_t r0, int64_t r1, floa
     return CAB_OK;
 }
 
+// ---- persistent index file ---------------------------------------------------------------------
+namespace {
+struct FileHeader {
+    char magic[8];
+    uint32_t version, dim, dtype, reserved;
+    uint64_t n_rows, row_base, off_asr, off_audio, off_flags, file_bytes;
+};
+constexpr char kMagic[8] = {'C', 'A', 'B', 'I', 'D', 'X', '0', '1'};
+constexpr size_t kFileAlign = 4096;
+constexpr size_t kIoChunk = size_t(32) << 20;
+
+int read_header(const char *path, FILE **fp, FileHeader *h, cab_index *idx) {
+    if (!path) return fail(idx, CAB_ERR_INVALID, "null path");
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail(idx, CAB_ERR_INVALID, "cannot open '%s' for reading", path);
+    uint8_t raw[kFileAlign];
+    if (fread(raw, 1, kFileAlign, f) != kFileAlign) { fclose(f); return fail(idx, CAB_ERR_INVALID, "'%s': truncated header", path); }
+    memcpy(h, raw, sizeof(FileHeader));
+    const size_t eb = h->dtype == CAB_BF16 ? 2 : 4;
+    bool ok = memcmp(h->magic, kMagic, 8) == 0 && h->version == 1 && h->dim == CAB_DIM &&
+              (h->dtype == CAB_F32 || h->dtype == CAB_BF16) && h->n_rows <= 0xFFFFFFF0ull &&
+              h->off_asr == kFileAlign && h->off_audio >= h->off_asr + h->n_rows * CAB_DIM * eb &&
+              h->off_flags >= h->off_audio + h->n_rows * CAB_DIM * eb && h->file_bytes >= h->off_flags + h->n_rows;
+    if (ok) {
+        fseek(f, 0, SEEK_END);
+        ok = uint64_t(ftell(f)) >= h->file_bytes;
+    }
+    if (!ok) { fclose(f); return fail(idx, CAB_ERR_INVALID, "'%s' is not a valid cab index file", path); }
+    *fp = f;
+    return CAB_OK;
+}
+}  // namespace
+
+int cab_index_file_info(const char *path, int *dim, int *dtype, int64_t *n_rows, int64_t *row_base) {
+    FILE *f = nullptr;
+    FileHeader h;
+    int rc = read_header(path, &f, &h, nullptr);
+    if (rc != CAB_OK) return rc;
+    fclose(f);
+    if (dim) *dim = int(h.dim);
+    if (dtype) *dtype = int(h.dtype);
+    if (n_rows) *n_rows = int64_t(h.n_rows);
+    if (row_base) *row_base = int64_t(h.row_base);
+    return CAB_OK;
+}
+
+int cab_index_save(cab_index *idx, const char *path) {
+    CHECK_HANDLE(idx);
+    if (!path) return fail(idx, CAB_ERR_INVALID, "null path");
+    CU(idx, cudaSetDevice(idx->device));
+    const size_t row_bytes = CAB_DIM * elem_size(idx->dtype);
+    const uint64_t n = uint64_t(idx->size);
+    FileHeader h{};
+    memcpy(h.magic, kMagic, 8);
+    h.version = 1; h.dim = CAB_DIM; h.dtype = uint32_t(idx->dtype); h.n_rows = n; h.row_base = uint64_t(idx->row_base);
+    h.off_asr = kFileAlign;
+    h.off_audio = align_up(h.off_asr + n * row_bytes, kFileAlign);
+    h.off_flags = align_up(h.off_audio + n * row_bytes, kFileAlign);
+    h.file_bytes = align_up(h.off_flags + n, kFileAlign);
+    int rc = ensure_pinned(idx, &idx->h_rows, &idx->h_rows_bytes, kIoChunk);
+    if (rc != CAB_OK) return rc;
+    FILE *f = fopen(path, "wb");
+    if (!f) return fail(idx, CAB_ERR_INVALID, "cannot open '%s' for writing", path);
+    std::vector<uint8_t> zeros(kFileAlign, 0);
+    memcpy(zeros.data(), &h, sizeof h);
+    bool ok = fwrite(zeros.data(), 1, kFileAlign, f) == kFileAlign;
+    memset(zeros.data(), 0, kFileAlign);
+    const struct { const void *src; uint64_t off, bytes; } sect[3] = {
+        {idx->asr, h.off_asr, n * row_bytes}, {idx->audio, h.off_audio, n * row_bytes}, {idx->flags, h.off_flags, n}};
+    uint64_t pos = kFileAlign;
+    for (int s3 = 0; s3 < 3 && ok; ++s3) {
+        for (; pos < sect[s3].off && ok; ) { size_t m = std::min<uint64_t>(kFileAlign, sect[s3].off - pos); ok = fwrite(zeros.data(), 1, m, f) == m; pos += m; }
+        for (uint64_t done = 0; done < sect[s3].bytes && ok; ) {
+            const size_t m = size_t(std::min<uint64_t>(kIoChunk, sect[s3].bytes - done));
+            cudaError_t e = cudaMemcpyAsync(idx->h_rows, static_cast<const uint8_t *>(sect[s3].src) + done, m, cudaMemcpyDeviceToHost, idx->own_stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(idx->own_stream);
+            if (e != cudaSuccess) { fclose(f); return fail(idx, CAB_ERR_CUDA, "save: %s", cudaGetErrorString(e)); }
+            ok = fwrite(idx->h_rows, 1, m, f) == m;
+            done += m; pos += m;
+        }
+    }
+    for (; pos < h.file_bytes && ok; ) { size_t m = std::min<uint64_t>(kFileAlign, h.file_bytes - pos); ok = fwrite(zeros.data(), 1, m, f) == m; pos += m; }
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) return fail(idx, CAB_ERR_INVALID, "write to '%s' failed", path);
+    return CAB_OK;
+}
+
+int cab_index_load(const char *path, int device, int64_t r0, int64_t r1, cab_index **out) {
+    if (!out) return fail(nullptr, CAB_ERR_INVALID, "out is null");
+    *out = nullptr;
+    FILE *f = nullptr;
+    FileHeader h;
+    int rc = read_header(path, &f, &h, nullptr);
+    if (rc != CAB_OK) return rc;
+    if (r1 < 0) r1 = int64_t(h.n_rows);
+    if (r0 < 0 || r0 > r1 || uint64_t(r1) > h.n_rows) { fclose(f); return fail(nullptr, CAB_ERR_INVALID, "row range [%lld, %lld) outside the file's %llu rows", (long long)r0, (long long)r1, (unsigned long long)h.n_rows); }
+    cab_index *idx = nullptr;
+    rc = cab_index_create(int(h.dim), int(h.dtype), r1 - r0, device, &idx);
+    if (rc != CAB_OK) { fclose(f); return rc; }
+    const size_t row_bytes = CAB_DIM * elem_size(idx->dtype);
+    const uint64_t n = uint64_t(r1 - r0);
+    rc = ensure_pinned(idx, &idx->h_rows, &idx->h_rows_bytes, kIoChunk);
+    const struct { void *dst; uint64_t off, bytes; } sect[3] = {
+        {idx->asr, h.off_asr + uint64_t(r0) * row_bytes, n * row_bytes},
+        {idx->audio, h.off_audio + uint64_t(r0) * row_bytes, n * row_bytes},
+        {idx->flags, h.off_flags + uint64_t(r0), n}};
+    for (int s3 = 0; s3 < 3 && rc == CAB_OK; ++s3) {
+        if (fseek(f, long(sect[s3].off), SEEK_SET) != 0) { rc = fail(nullptr, CAB_ERR_INVALID, "seek in '%s' failed", path); break; }
+        for (uint64_t done = 0; done < sect[s3].bytes; ) {
+            const size_t m = size_t(std::min<uint64_t>(kIoChunk, sect[s3].bytes - done));
+            if (fread(idx->h_rows, 1, m, f) != m) { rc = fail(nullptr, CAB_ERR_INVALID, "'%s': short read", path); break; }
+            cudaError_t e = cudaMemcpyAsync(static_cast<uint8_t *>(sect[s3].dst) + done, idx->h_rows, m, cudaMemcpyHostToDevice, idx->own_stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(idx->own_stream);
+            if (e != cudaSuccess) { rc = fail(nullptr, CAB_ERR_CUDA, "load: %s", cudaGetErrorString(e)); break; }
+            done += m;
+        }
+    }
+    fclose(f);
+    if (rc != CAB_OK) { cab_index_destroy(idx); return rc; }
+    idx->size = int64_t(n);
+    idx->row_base = int64_t(h.row_base) + r0;
+    *out = idx;
+    return CAB_OK;
+}
+
 // ---- search ------------------------------------------------------------------------------------
 struct OutLayout {
     size_t index, fusion, asr, audio, flags, count, nonfinite, total;

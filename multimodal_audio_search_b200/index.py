@@ -7,6 +7,7 @@ PyTorch is used only as the owner of device memory / streams -- all arithmetic i
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -54,6 +55,31 @@ class SegmentIndex:
         self.dtype = "bf16" if _DTYPES[dtype] == N.CAB_BF16 else "fp32"
         self.device = int(device)
         self.dim = dim
+
+    # -- persistence ---------------------------------------------------------------------------
+    def save(self, path: str):
+        """Write the index (normalised rows + flags exactly as in HBM) to `path`."""
+        N.check(self._lib.cab_index_save(self._h, os.fsencode(path)), self._h)
+
+    @classmethod
+    def load(cls, path: str, device: int = 0, rows: "tuple[int, int] | None" = None) -> "SegmentIndex":
+        """Load a saved index (or the row range `rows=(r0, r1)` of it: a shard) onto `device`."""
+        self = cls.__new__(cls)
+        self._lib = N.lib()
+        self._h = C.c_void_p()
+        r0, r1 = (0, -1) if rows is None else rows
+        N.check(self._lib.cab_index_load(os.fsencode(path), int(device), int(r0), int(r1), C.byref(self._h)))
+        self.dtype = "bf16" if self._lib.cab_index_dtype(self._h) == N.CAB_BF16 else "fp32"
+        self.device, self.dim = int(device), N.CAB_DIM
+        return self
+
+    @staticmethod
+    def file_info(path: str) -> dict:
+        """Header of a saved index without touching the GPU."""
+        dim, dtype, n, base = C.c_int(), C.c_int(), C.c_int64(), C.c_int64()
+        N.check(N.lib().cab_index_file_info(os.fsencode(path), C.byref(dim), C.byref(dtype), C.byref(n), C.byref(base)))
+        return {"dim": dim.value, "dtype": "bf16" if dtype.value == N.CAB_BF16 else "fp32",
+                "n_rows": n.value, "row_base": base.value}
 
     # -- lifetime ------------------------------------------------------------------------------
     def close(self):
