@@ -162,6 +162,43 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, E
         }
     }
 
+    // ---- counted lists (tensor-core scan): lists are mostly empty (tens of entries in 256 slots),
+    // so index the VALID entries through a prefix sum of the counts instead of walking every slot.
+    if (!done && counts) {
+        int *s_pref = reinterpret_cast<int *>(s_head);                 // s_head is unused on this path
+        const int P = a.n_partials < 2 * kMaxHeads - 1 ? a.n_partials : 2 * kMaxHeads - 1;
+        for (int j = threadIdx.x; j < P; j += kFinThreads) {
+            const int c = counts[j];
+            s_pref[j + 1] = c < a.slot_stride ? c : a.slot_stride;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { s_pref[0] = 0; for (int j = 0; j < P; ++j) s_pref[j + 1] += s_pref[j]; }
+        __syncthreads();
+        const int T = s_pref[P];
+        for (int base = 0; base < T; base += kFinThreads * kFinUnroll) {
+            uint64_t key[kFinUnroll];
+#pragma unroll
+            for (int u = 0; u < kFinUnroll; ++u) {
+                const int t = base + u * kFinThreads + threadIdx.x;
+                key[u] = 0ull;
+                if (t < T) {
+                    int lo = 0, hi = P;                                // largest l with s_pref[l] <= t
+                    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_pref[mid] <= t) lo = mid; else hi = mid; }
+                    key[u] = slots[size_t(lo) * a.slot_stride + (t - s_pref[lo])];
+                }
+            }
+            const uint64_t bound = s_bound;
+#pragma unroll
+            for (int u = 0; u < kFinUnroll; ++u) append(key[u] > bound, key[u]);
+            __syncthreads();
+            const bool full = s_cnt > kSortCap - kFinThreads * kFinUnroll;
+            __syncthreads();
+            if (full) trim();
+        }
+        trim();
+        done = true;
+    }
+
     // ---- general path: stream all slots (empty slots hold 0) through the buffer, sorting and
     // trimming to the best k whenever it fills ----------------------------------------------------
     if (!done) {
@@ -170,9 +207,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, E
 #pragma unroll
             for (int u = 0; u < kFinUnroll; ++u) {
                 const int i = base + u * kFinThreads + threadIdx.x;
-                bool in = i < total;
-                if (in && counts) { const int list = i / a.slot_stride; in = i - list * a.slot_stride < counts[list]; }
-                key[u] = in ? slots[i] : 0ull;
+                key[u] = i < total ? slots[i] : 0ull;
             }
             const uint64_t bound = s_bound;
 #pragma unroll
