@@ -191,6 +191,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--option", action="append", default=[], help="key=value engine option")
     ap.add_argument("--threshold", type=float, default=0.1, help="relevance threshold (reference: 0.1)")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: candidate exchange fused into the kernels over NVLink peer memory, or NCCL all-gather")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -227,7 +229,7 @@ def main():
     wa_all = np.array([w_classes[i % len(w_classes)] for i in range(n_steps * nq)])
     wb_all = 1.0 - wa_all
     q_dev = torch.from_numpy(q_host).cuda()
-    sharded = ShardedSearcher(idx, rank, world)
+    sharded = ShardedSearcher(idx, rank, world, exchange=args.exchange, max_queries=max(nq, 1), max_k=k)
 
     def step_device(i):
         sl = slice(i * nq, (i + 1) * nq)
@@ -325,7 +327,10 @@ def main():
             "config": {"workload": args.workload, "segments_per_gpu": n_rows, "global_segments": n_total,
                        "queries_per_step": nq, "k": k, "path": path, "threshold": args.threshold,
                        "l2": "inputs larger than L2 (corpus bytes per GPU >> 126 MB)",
-                       "exchange": "none" if world == 1 else "all_gather of per-shard top-k (24 B x k x Q per rank) + device merge",
+                       "exchange": "none" if world == 1 else (
+                           "per-shard top-k (24 B x k x Q per rank) stored into every rank's buffer over NVLink peer memory "
+                           "inside the finalize kernel + flag wait in the merge kernel" if args.exchange == "p2p" else
+                           "NCCL all_gather of per-shard top-k (24 B x k x Q per rank) + device merge"),
                        "value_definition": "queries/s x global_segments/1e6"},
             "queries_per_s": nq * 1e3 / ms_step, "hbm_gbs_all_gpus": world * alg_bytes * nq / (ms_step * 1e-3) / 1e9,
             "e2e": {"value": e2e_value, "unit": "queries/s (per 1M segments)", "ms_per_step": e2e_s / args.steps * 1e3,

@@ -161,6 +161,25 @@ CAB_API int cab_merge_candidates(cab_index *idx, const cab_candidate *cands_devi
                          float *out_audio, uint8_t *out_flags, int32_t *out_count, int out_loc,
                          void *stream);
 
+/* ---- sharded search with the exchange fused into the kernels (NVLink peer memory) ---------------
+ * Instead of steps 2+3 above through NCCL: the finalize kernel of every rank stores its k
+ * candidates per query straight into EVERY rank's exchange buffer (peer stores over NVLink /
+ * NVSwitch) and then raises a per-rank epoch flag; the merge kernel waits for the world's flags
+ * and merges.  One process per GPU; buffers are shared through CUDA IPC handles that the host
+ * side exchanges once (any transport; sharded.py uses torch.distributed).
+ *   cab_peer_init   : allocate this rank's exchange buffer, return its 64-byte IPC handle
+ *   cab_peer_attach : open all ranks' handles (world x 64 bytes, rank order)
+ *   cab_search_sharded : collective -- every rank calls it with the same n_queries / k / path.
+ *                     Outputs as cab_search; every rank receives the same merged result. */
+#define CAB_IPC_HANDLE_BYTES 64
+#define CAB_MAX_WORLD 8
+CAB_API int cab_peer_init(cab_index *idx, int rank, int world, int max_queries, int max_k, void *ipc_handle_out);
+CAB_API int cab_peer_attach(cab_index *idx, const void *all_handles);
+CAB_API int cab_search_sharded(cab_index *idx, const float *queries, int queries_loc, const double *w_asr,
+                               const double *w_audio, int n_queries, int k, double threshold, int path,
+                               int64_t *out_index, double *out_fusion, float *out_asr, float *out_audio,
+                               uint8_t *out_flags, int32_t *out_count, int out_loc, void *stream);
+
 /* ---- tuning / introspection -------------------------------------------------------------- */
 /* Options: "gemv_unroll" (row-steps in flight per warp: 1/2/4/8, 0 = default),
  * "gemv_blocks_per_sm" (resident CTAs per SM, 0 = default), "gemv_batch", "gemm_min_queries",

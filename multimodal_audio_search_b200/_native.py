@@ -19,6 +19,7 @@ CAB_HOST, CAB_DEVICE = 0, 1
 CAB_PATH_AUTO, CAB_PATH_GEMV, CAB_PATH_GEMM = 0, 1, 2
 CAB_DIM, CAB_MAX_K, CAB_MAX_QUERIES = 384, 128, 4096
 CANDIDATE_BYTES = 24
+CAB_IPC_HANDLE_BYTES, CAB_MAX_WORLD = 64, 8
 
 
 class NativeLibraryMissing(RuntimeError):
@@ -61,6 +62,9 @@ SIGNATURES = {
     "cab_search": (_i32, [_p, _p, _i32, _p, _p, _i32, _i32, _dbl, _i32, _p, _p, _p, _p, _p, _p, _i32, _p]),
     "cab_search_candidates": (_i32, [_p, _p, _i32, _p, _p, _i32, _i32, _dbl, _i32, _p, _p]),
     "cab_merge_candidates": (_i32, [_p, _p, _i32, _i32, _i32, _p, _p, _dbl, _p, _p, _p, _p, _p, _p, _i32, _p]),
+    "cab_peer_init": (_i32, [_p, _i32, _i32, _i32, _i32, _p]),
+    "cab_peer_attach": (_i32, [_p, _p]),
+    "cab_search_sharded": (_i32, [_p, _p, _i32, _p, _p, _i32, _i32, _dbl, _i32, _p, _p, _p, _p, _p, _p, _i32, _p]),
     "cab_index_set_option": (_i32, [_p, C.c_char_p, _i64]),
     "cab_index_get_option": (_i64, [_p, C.c_char_p]),
     "cab_index_launch_count": (_i64, [_p]),

@@ -58,6 +58,14 @@ struct cab_index {
     GemvConfig gemv{0, 0, 0};
     int64_t opt_time_kernels = 0, opt_sync = 0, opt_gemm_min_queries = 64, opt_gemv_batch = 32;
     int64_t opt_finalize_general = 0;
+    // peer-memory exchange (sharded search)
+    int peer_world = 0, peer_rank = 0, peer_qcap = 0, peer_kcap = 0;
+    bool peer_attached = false;
+    uint8_t *d_peer = nullptr;                       // [flags 2 x world u32 | pad to 256][cands 2 x world x qcap x kcap]
+    uint8_t *peer_ptr[CAB_MAX_WORLD] = {};           // every rank's buffer as mapped in this process
+    uint32_t peer_epoch = 0;
+    unsigned int *d_done = nullptr;
+    int *d_status = nullptr;
     int64_t launches = 0;
     std::string err;
     int sticky = CAB_OK;
@@ -185,6 +193,9 @@ int cab_index_destroy(cab_index *idx) {
     cudaFree(idx->d_params);
     cudaFree(idx->d_partial_keys); cudaFree(idx->d_cands);
     cudaFree(idx->d_out); cudaFree(idx->d_gemm_ws); cudaFree(idx->d_nonfinite); cudaFree(idx->d_rows); cudaFree(idx->d_counters);
+    for (int r = 0; r < idx->peer_world; ++r)
+        if (idx->peer_attached && r != idx->peer_rank && idx->peer_ptr[r]) cudaIpcCloseMemHandle(idx->peer_ptr[r]);
+    cudaFree(idx->d_peer); cudaFree(idx->d_done); cudaFree(idx->d_status);
     cudaFreeHost(idx->h_in); cudaFreeHost(idx->h_out); cudaFreeHost(idx->h_rows);
     if (idx->ev_in) cudaEventDestroy(idx->ev_in);
     if (idx->ev_t0) cudaEventDestroy(idx->ev_t0);
@@ -607,7 +618,7 @@ struct UserOut {
 };
 static int run_local(cab_index *idx, const float *queries, int queries_loc, const double *w_asr,
                      const double *w_audio, int nq, int k, double threshold, int path,
-                     const UserOut *out, cab_candidate *cand_dst, cudaStream_t s) {
+                     const UserOut *out, cab_candidate *cand_dst, const PeerPush *peer, cudaStream_t s) {
     if (!queries || !w_asr || !w_audio) return fail(idx, CAB_ERR_INVALID, "queries / weights are null");
     if (queries_loc != CAB_HOST && queries_loc != CAB_DEVICE) return fail(idx, CAB_ERR_INVALID, "queries_loc");
     if (nq <= 0 || nq > CAB_MAX_QUERIES) return fail(idx, CAB_ERR_INVALID, "n_queries must be in 1..%d", CAB_MAX_QUERIES);
@@ -645,6 +656,7 @@ static int run_local(cab_index *idx, const float *queries, int queries_loc, cons
         // nothing to scan: every candidate slot is empty
         CU(idx, cudaMemsetAsync(cands, 0xFF, size_t(nq) * k * sizeof(cab_candidate), s));
         if (out) { ea.cands = cands; launch_emit(ea, s); idx->launches += 1; CU(idx, cudaGetLastError()); }
+        if (peer) { PeerPush pp = *peer; pp.q0 = 0; pp.signal = 1; launch_peer_push(cands, nq, k, pp, s); idx->launches += 1; CU(idx, cudaGetLastError()); }
         return CAB_OK;
     }
 
@@ -676,6 +688,7 @@ static int run_local(cab_index *idx, const float *queries, int queries_loc, cons
         }
         if (idx->opt_time_kernels && q0 + batch >= nq) CU(idx, cudaEventRecord(idx->ev_t1, s));
         fa.queries = sa.queries; fa.n_queries = m; fa.cands = cands + size_t(q0) * k;
+        if (peer) { fa.peer = *peer; fa.peer.q0 = q0; fa.peer.signal = q0 + batch >= nq ? 1 : 0; }
         if (out) {
             EmitArgs eb = ea;                           // this batch's slice of the outputs
             eb.n_queries = m;
@@ -730,7 +743,7 @@ int cab_search(cab_index *idx, const float *queries, int queries_loc, const doub
     CHECK_HANDLE(idx);
     cudaStream_t s = stream ? (cudaStream_t)stream : idx->own_stream;
     const UserOut o{out_index, out_fusion, out_asr, out_audio, out_flags, out_count, out_loc};
-    int rc = run_local(idx, queries, queries_loc, w_asr, w_audio, n_queries, k, threshold, path, &o, nullptr, s);
+    int rc = run_local(idx, queries, queries_loc, w_asr, w_audio, n_queries, k, threshold, path, &o, nullptr, nullptr, s);
     if (rc != CAB_OK) return rc;
     return finish_outputs(idx, n_queries, k, o, s);
 }
@@ -741,7 +754,7 @@ int cab_search_candidates(cab_index *idx, const float *queries, int queries_loc,
     CHECK_HANDLE(idx);
     if (!out_device) return fail(idx, CAB_ERR_INVALID, "out_device is null");
     cudaStream_t s = stream ? (cudaStream_t)stream : idx->own_stream;
-    int rc = run_local(idx, queries, queries_loc, w_asr, w_audio, n_queries, k, threshold, path, nullptr, out_device, s);
+    int rc = run_local(idx, queries, queries_loc, w_asr, w_audio, n_queries, k, threshold, path, nullptr, out_device, nullptr, s);
     if (rc != CAB_OK) return rc;
     if (idx->opt_sync) CU(idx, cudaStreamSynchronize(s));
     return CAB_OK;
@@ -768,6 +781,85 @@ int cab_merge_candidates(cab_index *idx, const cab_candidate *cands_device, int 
     EmitArgs ea = make_emit(idx, n_lists, n_queries, k, threshold, out_index, out_fusion, out_asr,
                             out_audio, out_flags, out_count, out_loc);
     ea.cands = cands_device;
+    launch_emit(ea, s);
+    idx->launches += 1;
+    CU(idx, cudaGetLastError());
+    return finish_outputs(idx, n_queries, k, o, s);
+}
+
+// ---- peer-memory exchange ----------------------------------------------------------------------
+static size_t peer_flags_bytes() { return 256; }
+static size_t peer_half_elems(const cab_index *idx) { return size_t(idx->peer_world) * idx->peer_qcap * idx->peer_kcap; }
+
+int cab_peer_init(cab_index *idx, int rank, int world, int max_queries, int max_k, void *ipc_handle_out) {
+    CHECK_HANDLE(idx);
+    if (!ipc_handle_out || world < 1 || world > CAB_MAX_WORLD || rank < 0 || rank >= world ||
+        max_queries < 1 || max_queries > CAB_MAX_QUERIES || max_k < 1 || max_k > CAB_MAX_K)
+        return fail(idx, CAB_ERR_INVALID, "bad peer_init arguments");
+    if (idx->d_peer) return fail(idx, CAB_ERR_INVALID, "peer exchange already initialised on this index");
+    static_assert(sizeof(cudaIpcMemHandle_t) == CAB_IPC_HANDLE_BYTES, "IPC handle size");
+    CU(idx, cudaSetDevice(idx->device));
+    idx->peer_world = world; idx->peer_rank = rank; idx->peer_qcap = max_queries; idx->peer_kcap = max_k;
+    const size_t bytes = peer_flags_bytes() + 2 * peer_half_elems(idx) * sizeof(cab_candidate);
+    CU(idx, cudaMalloc((void **)&idx->d_peer, bytes));
+    CU(idx, cudaMemset(idx->d_peer, 0, bytes));
+    CU(idx, cudaMalloc((void **)&idx->d_done, sizeof(unsigned int)));
+    CU(idx, cudaMemset(idx->d_done, 0, sizeof(unsigned int)));
+    CU(idx, cudaMalloc((void **)&idx->d_status, sizeof(int)));
+    CU(idx, cudaMemset(idx->d_status, 0, sizeof(int)));
+    CU(idx, cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    CU(idx, cudaIpcGetMemHandle(&h, idx->d_peer));
+    memcpy(ipc_handle_out, &h, sizeof h);
+    return CAB_OK;
+}
+
+int cab_peer_attach(cab_index *idx, const void *all_handles) {
+    CHECK_HANDLE(idx);
+    if (!idx->d_peer || !all_handles) return fail(idx, CAB_ERR_INVALID, "cab_peer_init first");
+    if (idx->peer_attached) return fail(idx, CAB_ERR_INVALID, "peers already attached");
+    CU(idx, cudaSetDevice(idx->device));
+    for (int r = 0; r < idx->peer_world; ++r) {
+        if (r == idx->peer_rank) { idx->peer_ptr[r] = idx->d_peer; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const uint8_t *>(all_handles) + size_t(r) * CAB_IPC_HANDLE_BYTES, sizeof h);
+        void *ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(idx, CAB_ERR_CUDA, "cannot map rank %d's exchange buffer: %s", r, cudaGetErrorString(e)); }
+        idx->peer_ptr[r] = static_cast<uint8_t *>(ptr);
+    }
+    idx->peer_attached = true;
+    return CAB_OK;
+}
+
+int cab_search_sharded(cab_index *idx, const float *queries, int queries_loc, const double *w_asr,
+                       const double *w_audio, int n_queries, int k, double threshold, int path,
+                       int64_t *out_index, double *out_fusion, float *out_asr, float *out_audio,
+                       uint8_t *out_flags, int32_t *out_count, int out_loc, void *stream) {
+    CHECK_HANDLE(idx);
+    if (!idx->peer_attached) return fail(idx, CAB_ERR_INVALID, "cab_peer_init / cab_peer_attach first");
+    if (n_queries > idx->peer_qcap || k > idx->peer_kcap)
+        return fail(idx, CAB_ERR_INVALID, "n_queries / k exceed the exchange buffer (%d x %d)", idx->peer_qcap, idx->peer_kcap);
+    cudaStream_t s = stream ? (cudaStream_t)stream : idx->own_stream;
+    const uint32_t epoch = ++idx->peer_epoch;
+    PeerPush pp{};
+    pp.world = idx->peer_world; pp.rank = idx->peer_rank; pp.parity = int(epoch & 1u); pp.epoch = epoch;
+    pp.n_queries_total = n_queries; pp.done_counter = idx->d_done;
+    const size_t half = peer_half_elems(idx);
+    for (int r = 0; r < idx->peer_world; ++r) {
+        pp.flags[r] = reinterpret_cast<uint32_t *>(idx->peer_ptr[r]);
+        pp.bufs[r] = reinterpret_cast<cab_candidate *>(idx->peer_ptr[r] + peer_flags_bytes()) + size_t(pp.parity) * half;
+    }
+    int rc = run_local(idx, queries, queries_loc, w_asr, w_audio, n_queries, k, threshold, path, nullptr, nullptr, &pp, s);
+    if (rc != CAB_OK) return rc;
+    const UserOut o{out_index, out_fusion, out_asr, out_audio, out_flags, out_count, out_loc};
+    if (out_loc != CAB_HOST && out_loc != CAB_DEVICE) return fail(idx, CAB_ERR_INVALID, "out_loc");
+    EmitArgs ea = make_emit(idx, idx->peer_world, n_queries, k, threshold, out_index, out_fusion, out_asr,
+                            out_audio, out_flags, out_count, out_loc);
+    ea.cands = pp.bufs[idx->peer_rank];
+    ea.wait_flags = pp.flags[idx->peer_rank] + pp.parity * idx->peer_world;
+    ea.wait_epoch = epoch;
+    ea.status = idx->d_status;
     launch_emit(ea, s);
     idx->launches += 1;
     CU(idx, cudaGetLastError());

@@ -67,6 +67,47 @@ __device__ __forceinline__ void block_sort_results(uint64_t *score, int64_t *ind
     __syncthreads();
 }
 
+// ---- peer-memory exchange helpers ----------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// Slot of candidate i of query q (index within the whole call) of rank `rank` in an exchange buffer.
+__device__ __forceinline__ size_t peer_slot(const PeerPush &p, int q, int k, int i) {
+    return (size_t(p.rank) * p.n_queries_total + q) * k + i;
+}
+// After every CTA of the (last) launch has stored its candidates on all ranks: raise this rank's
+// epoch flag on every rank.  Called by all threads of every CTA.
+__device__ __forceinline__ void peer_signal(const PeerPush &p) {
+    __threadfence_system();                       // this thread's peer stores are performed system-wide
+    __syncthreads();
+    if (threadIdx.x == 0 && p.signal) {
+        const unsigned prev = atomicAdd(p.done_counter, 1u);
+        if (prev == gridDim.x - 1) {              // last CTA: everyone's stores are ordered before this
+            *p.done_counter = 0u;
+            __threadfence_system();
+            for (int r = 0; r < p.world; ++r) st_release_sys(p.flags[r] + p.parity * p.world + p.rank, p.epoch);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) peer_push_kernel(const cab_candidate *__restrict__ local, int n_queries, int k, PeerPush p) {
+    const int total = n_queries * k;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const cab_candidate c = local[t];
+        const size_t slot = peer_slot(p, p.q0 + t / k, k, t % k);
+        for (int r = 0; r < p.world; ++r) p.bufs[r][slot] = c;
+    }
+    peer_signal(p);
+}
+void launch_peer_push(const cab_candidate *local, int n_queries, int k, const PeerPush &peer, cudaStream_t s) {
+    peer_push_kernel<<<1, 256, 0, s>>>(local, n_queries, k, peer);
+}
+
 // ---- finalize ---------------------------------------------------------------------------------
 template <int DT>
 __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, EmitArgs e) {
@@ -252,9 +293,14 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, E
             c.pad = 0u;
             out[i] = c;
             s_cand[i] = c;
+            if (a.peer.world) {                            // sharded search: store on every rank over NVLink
+                const size_t slot = peer_slot(a.peer, a.peer.q0 + qi, a.k, i);
+                for (int r = 0; r < a.peer.world; ++r) a.peer.bufs[r][slot] = c;
+            }
         }
     }
-    if (!e.out_index) return;          // sharded search: candidates go to the all-gather
+    if (a.peer.world) peer_signal(a.peer);
+    if (!e.out_index) return;          // sharded search: candidates go to the exchange
 
     // ---- fused emit (single candidate list): rank the <= k candidates by counting ----------------
     __syncthreads();
@@ -318,6 +364,20 @@ __global__ void __launch_bounds__(kEmitThreads) emit_kernel(EmitArgs a) {
     while (np2 < n_cand) np2 <<= 1;
     const double wa = a.w_asr[qi], wb = a.w_audio[qi];
     if (threadIdx.x == 0) s_n = 0;
+    if (a.wait_flags) {
+        // peer exchange: every rank's candidates of this epoch must have landed in our buffer
+        if (threadIdx.x < a.n_lists) {
+            const long long t0 = clock64();
+            while (ld_acquire_sys(a.wait_flags + threadIdx.x) != a.wait_epoch) {
+                if (clock64() - t0 > 20000000000ll) {          // ~10 s: a rank never arrived
+                    if (a.status) atomicExch(a.status, 7);
+                    __threadfence_system();
+                    asm volatile("trap;");
+                }
+            }
+        }
+        __syncthreads();
+    }
     // candidate t of this query lives at list-major position:
     auto cand_at = [&](int t) -> const cab_candidate * {
         const int list = t / a.k, i = t - list * a.k;

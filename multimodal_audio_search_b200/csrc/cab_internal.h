@@ -62,6 +62,19 @@ constexpr int kGemmListCap = 256;       // slots per (CTA pair, query) candidate
 constexpr int kGemmQueriesPerPass = 256;
 
 // ---- finalize + emit (cab_finalize.cu) ----------------------------------------------------------
+// Peer-memory exchange (sharded search): where the finalize kernel also stores this rank's
+// candidates, and the epoch flag it raises on every rank when all of them are written.
+struct PeerPush {
+    int world;                       // 0 = no peer exchange
+    int rank;
+    int parity;                      // exchange buffers are double-buffered by epoch parity
+    int signal;                      // raise the flags at the end of this launch
+    int q0, n_queries_total;         // this launch handles queries [q0, q0 + n_queries) of the call
+    uint32_t epoch;
+    cab_candidate *bufs[CAB_MAX_WORLD];   // rank r's buffer: [2][world][n_queries_total][k]
+    uint32_t *flags[CAB_MAX_WORLD];       // rank r's flags:  [2][world]
+    unsigned int *done_counter;      // local: CTAs of this launch that finished pushing
+};
 struct FinalizeArgs {
     const void *asr;
     const void *audio;
@@ -82,6 +95,7 @@ struct FinalizeArgs {
     cab_candidate *cands;      // out [n_queries][k], best-first by scan score, index -1 = empty
     int force_general;         // test hook: skip the head-bound fast path
     unsigned int *work_counters;   // [n_queries] reset to 0 for the next scan (may be null)
+    PeerPush peer;
 };
 struct EmitArgs;
 // fused_emit != nullptr (single candidate list): the emit stage runs inside the same kernel.
@@ -103,7 +117,14 @@ struct EmitArgs {
     int32_t *out_count;
     const int *nonfinite;         // device flag set by scan / ingest kernels
     int *nonfinite_out;           // copy of it next to the outputs (may be null)
+    // peer exchange: wait until wait_flags[0..n_lists) all hold wait_epoch before reading cands
+    const uint32_t *wait_flags;   // null = no wait
+    uint32_t wait_epoch;
+    int *status;                  // set to 7 (and the kernel traps) if the wait times out
 };
+// Push a local candidate block [n_queries x k] to every peer and raise the flags (used when there
+// was nothing to scan; otherwise the finalize kernel pushes).
+void launch_peer_push(const cab_candidate *local, int n_queries, int k, const PeerPush &peer, cudaStream_t s);
 void launch_emit(const EmitArgs &a, cudaStream_t s);
 
 }  // namespace cab

@@ -261,6 +261,49 @@ class SegmentIndex:
         return out
 
 
+    # -- sharded search with the exchange fused into the kernels (NVLink peer memory) -----------
+    def peer_init(self, rank: int, world: int, max_queries: int = 256, max_k: int = N.CAB_MAX_K) -> bytes:
+        """Allocate this rank's exchange buffer; returns its 64-byte CUDA IPC handle."""
+        buf = C.create_string_buffer(N.CAB_IPC_HANDLE_BYTES)
+        N.check(self._lib.cab_peer_init(self._h, int(rank), int(world), int(max_queries), int(max_k), buf), self._h)
+        return buf.raw
+
+    def peer_attach(self, all_handles: bytes):
+        """Map every rank's exchange buffer (handles concatenated in rank order)."""
+        N.check(self._lib.cab_peer_attach(self._h, C.c_char_p(all_handles)), self._h)
+
+    def search_sharded(self, queries, w_asr=0.5, w_audio=0.5, k: int = 10, threshold: float = 0.1,
+                       path: str = "auto", to_host: bool = True) -> SearchResult:
+        """Collective: every rank calls it with the same shapes; the per-shard top-k travel over
+        peer memory inside the finalize kernel; every rank gets the merged result."""
+        import torch
+        if _is_torch_cuda(queries):
+            q = queries if queries.dim() == 2 else queries.unsqueeze(0)
+            qp, qloc, nq, stream = C.c_void_p(q.data_ptr()), N.CAB_DEVICE, q.shape[0], self._stream()
+        else:
+            q = _np_f32(np.atleast_2d(queries), self.dim)
+            qp, qloc, nq, stream = _ptr(q), N.CAB_HOST, q.shape[0], (None if to_host else self._stream())
+        wa, wb = self._weights(w_asr, w_audio, nq)
+        if to_host:
+            out = SearchResult(np.empty((nq, k), np.int64), np.empty((nq, k), np.float64),
+                               np.empty((nq, k), np.float32), np.empty((nq, k), np.float32),
+                               np.empty((nq, k), np.uint8), np.empty((nq,), np.int32))
+            p, loc = _ptr, N.CAB_HOST
+        else:
+            dev = f"cuda:{self.device}"
+            out = SearchResult(torch.empty((nq, k), dtype=torch.int64, device=dev),
+                               torch.empty((nq, k), dtype=torch.float64, device=dev),
+                               torch.empty((nq, k), dtype=torch.float32, device=dev),
+                               torch.empty((nq, k), dtype=torch.float32, device=dev),
+                               torch.empty((nq, k), dtype=torch.uint8, device=dev),
+                               torch.empty((nq,), dtype=torch.int32, device=dev))
+            p, loc = (lambda t: C.c_void_p(t.data_ptr())), N.CAB_DEVICE
+        N.check(self._lib.cab_search_sharded(self._h, qp, qloc, _ptr(wa), _ptr(wb), nq, k, float(threshold),
+                                             _PATHS[path], p(out.indices), p(out.fusion), p(out.asr_sim),
+                                             p(out.audio_sim), p(out.flags), p(out.count), loc, stream), self._h)
+        return out
+
+
 def synth_queries(seed: int, q0: int, q1: int, device: int = 0) -> np.ndarray:
     """Raw synthetic query vectors generated by the device twin of synth.raw_queries."""
     out = np.empty((q1 - q0, N.CAB_DIM), dtype=np.float32)

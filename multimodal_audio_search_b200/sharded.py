@@ -4,8 +4,12 @@ Each rank owns the contiguous global segment range `shard_range(n_total, rank, w
 `SegmentIndex` (with `row_base` = first global segment), so a search is:
 
   1. local fused scan -> this shard's top-k as packed 24-byte candidates   (libcab, on device)
-  2. ONE all-gather of the candidate blocks  [world, Q, k, 24]            (NCCL over NVLink;
-     <= 24 B x k x Q per rank: latency-bound, it is the path's only exchange step)
+  2. ONE exchange of the candidate blocks  [world, Q, k, 24]  (<= 24 B x k x Q per rank:
+     latency-bound, the path's only exchange step), either
+       exchange="p2p"  (default on GPUs): fused into the finalize kernel -- every rank stores its
+                       candidates straight into every rank's buffer over NVLink peer memory
+                       (CUDA IPC) and raises an epoch flag; the merge kernel waits on the flags;
+       exchange="nccl": torch.distributed.all_gather_into_tensor (also what the gloo CPU test uses)
   3. merge on every rank: float64 reference fusion, threshold, (score desc, global index asc),
      first k                                                              (libcab, on device)
 
@@ -33,14 +37,31 @@ class ShardedSearcher:
     """Drives steps 1-3 for one rank.  `index` is this rank's SegmentIndex (or any object with
     `search_candidates` / `merge_candidates`); `group` a torch.distributed process group."""
 
-    def __init__(self, index, rank: int = 0, world: int = 1, group=None):
+    def __init__(self, index, rank: int = 0, world: int = 1, group=None, exchange: str = "nccl",
+                 max_queries: int = 256, max_k: int = 128):
         self.index, self.rank, self.world, self.group = index, rank, world, group
         self._gathered = None
+        self.exchange = exchange if world > 1 else "nccl"
+        if self.exchange not in ("nccl", "p2p"):
+            raise ValueError("exchange must be 'nccl' or 'p2p'")
+        self.max_queries, self.max_k = max_queries, max_k
+        if self.exchange == "p2p":
+            import torch.distributed as dist
+            handle = index.peer_init(rank, world, max_queries, max_k)
+            handles = [None] * world
+            dist.all_gather_object(handles, handle, group=group)      # host-side, once
+            index.peer_attach(b"".join(handles))
+            dist.barrier(group=group)
 
     def search(self, queries, w_asr, w_audio, k: int = 10, threshold: float = 0.1, path: str = "auto",
                to_host: bool = True):
         import torch
         import torch.distributed as dist
+        if self.exchange == "p2p":
+            n = queries.shape[0] if hasattr(queries, "shape") and len(queries.shape) == 2 else 1
+            if n <= self.max_queries and k <= self.max_k:
+                return self.index.search_sharded(queries, w_asr, w_audio, k=k, threshold=threshold, path=path,
+                                                 to_host=to_host)
         cands = self.index.search_candidates(queries, w_asr, w_audio, k=k, threshold=threshold, path=path)
         if self.world == 1:
             gathered = cands.unsqueeze(0)
