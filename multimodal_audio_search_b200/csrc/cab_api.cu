@@ -55,7 +55,7 @@ struct cab_index {
     cudaEvent_t ev_in = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     bool ev_in_pending = false, timed = false;
     // options
-    GemvConfig gemv{0, 0, 0};
+    GemvConfig gemv{0, 0, 0, 0};
     int64_t opt_time_kernels = 0, opt_sync = 0, opt_gemm_min_queries = 64, opt_gemv_batch = 32;
     int64_t opt_finalize_general = 0;
     // peer-memory exchange (sharded search)
@@ -638,8 +638,7 @@ static int run_local(cab_index *idx, const float *queries, int queries_loc, cons
         use_gemm = idx->dtype == CAB_BF16 && nq >= idx->opt_gemm_min_queries && gemm_path_available();
     }
     CU(idx, cudaSetDevice(idx->device));
-    const int n_partials = use_gemm ? gemm_partials_per_query(idx->sm_count)
-                                    : gemv_grid_size(idx->gemv, idx->dtype, idx->sm_count);
+    const int n_partials = use_gemm ? gemm_partials_per_query(idx->sm_count) : gemv_max_grid(idx->sm_count);
     const int batch = use_gemm ? std::min(nq, kGemmQueriesPerPass) : int(std::min<int64_t>(nq, idx->opt_gemv_batch));
     int rc = ensure_workspace(idx, nq, k, n_partials, use_gemm ? kGemmQueriesPerPass : batch,
                               use_gemm ? kGemmListCap : k, use_gemm ? gemm_workspace_bytes(nq, k, idx->sm_count) : 0);
@@ -684,7 +683,9 @@ static int run_local(cab_index *idx, const float *queries, int queries_loc, cons
             launch_gemm_scan(sa, idx->sm_count, idx->d_gemm_ws, idx->d_gemm_ws_bytes, s, &err);
             if (!err.empty()) return fail(idx, CAB_ERR_CUDA, "%s", err.c_str());
         } else {
-            launch_gemv_scan(sa, idx->gemv, idx->sm_count, s);
+            const GemvPlan plan = plan_gemv(idx->gemv, idx->dtype, m, idx->sm_count);
+            sa.n_partials = fa.n_partials = plan.grid_x;
+            launch_gemv_scan(sa, plan, s);
         }
         if (idx->opt_time_kernels && q0 + batch >= nq) CU(idx, cudaEventRecord(idx->ev_t1, s));
         fa.queries = sa.queries; fa.n_queries = m; fa.cands = cands + size_t(q0) * k;
@@ -873,6 +874,7 @@ int cab_index_set_option(cab_index *idx, const char *key, int64_t value) {
     if (k == "gemv_variant") { if (value != 0) return fail(idx, CAB_ERR_INVALID, "gemv_variant: only 0 (LDG register pipeline) is built"); idx->gemv.variant = int(value); }
     else if (k == "gemv_blocks_per_sm") { if (value < 0 || value > 8) return fail(idx, CAB_ERR_INVALID, "gemv_blocks_per_sm in 0..8"); idx->gemv.blocks_per_sm = int(value); }
     else if (k == "gemv_unroll") { if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) return fail(idx, CAB_ERR_INVALID, "gemv_unroll in {0,1,2,4,8}"); idx->gemv.unroll = int(value); }
+    else if (k == "gemv_query_tile") { if (value != 0 && value != 1 && value != 2 && value != 4) return fail(idx, CAB_ERR_INVALID, "gemv_query_tile in {0,1,2,4}"); idx->gemv.query_tile = int(value); }
     else if (k == "time_kernels") idx->opt_time_kernels = value != 0;
     else if (k == "sync_after_search") idx->opt_sync = value != 0;
     else if (k == "finalize_general") idx->opt_finalize_general = value != 0;
@@ -894,7 +896,8 @@ int64_t cab_index_get_option(const cab_index *idx, const char *key) {
     if (k == "gemm_min_queries") return idx->opt_gemm_min_queries;
     if (k == "gemv_batch") return idx->opt_gemv_batch;
     if (k == "sm_count") return idx->sm_count;
-    if (k == "gemv_grid") return gemv_grid_size(idx->gemv, idx->dtype, idx->sm_count);
+    if (k == "gemv_query_tile") return idx->gemv.query_tile;
+    if (k == "gemv_grid") return plan_gemv(idx->gemv, idx->dtype, 1, idx->sm_count).grid_x;
     return -1;
 }
 

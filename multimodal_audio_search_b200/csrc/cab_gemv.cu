@@ -31,29 +31,40 @@ __device__ __forceinline__ void keep_live(uint4 (&c)[3]) {
 
 // MB (min resident CTAs per SM) is part of the contract with ptxas: without it ptxas caps the
 // kernel at 80 registers and interleaves loads with FMAs (7 loads in flight instead of 24).
-template <int DT, int U, int MB>
+// QT = queries scored per corpus pass (register tiling): the rows are loaded once and multiplied
+// with QT query vectors held in registers, so a batch of fp32 queries costs one HBM pass per QT
+// queries instead of one per query (24*QT FFMA per lane per row-step stay far below the FMA pipe:
+// the kernel remains HBM-bound at QT = 4).
+template <int DT, int U, int MB, int QT>
 __global__ void __launch_bounds__(kScanThreads, MB)
 gemv_scan_kernel(ScanArgs a) {
     using TR = RowTraits<DT>;
     constexpr int G = TR::G, RW = TR::RW, CPR = TR::CPR;
     constexpr int kRowsPerIter = U * RW;
     constexpr int kOwnerLanes = G / U;            // lanes sharing one finished row
+    constexpr int NV = 2 * QT;                    // values per row-step: (s_asr, s_audio) per query
     static_assert(U == 1 || U == 2 || U == 4 || U == 8, "U");
 
-    __shared__ uint64_t s_keys[kScanWarps][kWarpCap];
-    __shared__ int s_count[kScanWarps];
+    extern __shared__ __align__(16) uint8_t scan_smem[];
+    uint64_t(*s_keys)[QT][kWarpCap] = reinterpret_cast<uint64_t(*)[QT][kWarpCap]>(scan_smem);
+    int(*s_count)[QT] = reinterpret_cast<int(*)[QT]>(scan_smem + sizeof(uint64_t) * kScanWarps * QT * kWarpCap);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int qi = blockIdx.y;
+    const int q0 = blockIdx.y * QT;               // first query of this CTA's group
     const int g = lane & (G - 1), sub = lane / G;
 
-    float q[TR::NQ];
-    bool ok = load_query<DT>(a.queries + size_t(qi) * kDim, lane, q);
-    if (!ok && lane == 0) *a.nonfinite = 1;
-    const ScanWeights w{a.wa32[qi], a.wb32[qi]};
-
-    WarpTopK top;
-    top.init(s_keys[warp], a.k, bound_key(a.select_threshold));
+    float q[QT][TR::NQ];
+    ScanWeights w[QT];
+    WarpTopK top[QT];
+#pragma unroll
+    for (int t = 0; t < QT; ++t) {
+        const bool valid = q0 + t < a.n_queries;
+        const int qi = valid ? q0 + t : q0;       // pad the group with its first query, never pushed
+        bool ok = load_query<DT>(a.queries + size_t(qi) * kDim, lane, q[t]);
+        if (!ok && lane == 0) *a.nonfinite = 1;
+        w[t] = ScanWeights{a.wa32[qi], a.wb32[qi]};
+        top[t].init(s_keys[warp][t], a.k, valid ? bound_key(a.select_threshold) : ~0ull);
+    }
 
     // Which of the U row-steps this lane ends up owning after the transposing reduction.
     int u_lane = 0;
@@ -70,12 +81,12 @@ gemv_scan_kernel(ScanArgs a) {
     const int64_t total_warps = int64_t(gridDim.x) * kScanWarps;
 
     // Dynamic chunk scheduling: a warp's first chunk is static (its global warp id); every further
-    // chunk comes from a per-query atomic counter, fetched one chunk ahead so the atomic's latency
+    // chunk comes from a per-group atomic counter, fetched one chunk ahead so the atomic's latency
     // is hidden.  Unlike a static split this tolerates SMs that are late or busy (another kernel,
     // e.g. an NCCL collective, holding an SM) and evens out SM-to-SM speed differences.
     constexpr int kChunkRows = kRowsPerIter * (64 / kRowsPerIter);      // 64 rows per chunk
     const int64_t n_chunks = (n + kChunkRows - 1) / kChunkRows;
-    unsigned int *counter = a.work_counters + qi;
+    unsigned int *counter = a.work_counters + blockIdx.y;
     int64_t chunk = gwarp;
     unsigned int ticket = 0;                                  // lane 0: result of the in-flight atomic
     if (chunk < n_chunks && lane == 0) ticket = atomicAdd(counter, 1u);
@@ -100,14 +111,16 @@ gemv_scan_kernel(ScanArgs a) {
 #pragma unroll
         for (int u = 0; u < U; ++u) { keep_live(ca[u]); keep_live(cb[u]); }
 
-        float v[U][2];
+        float v[U][NV];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            float sa = 0.f, sb = 0.f;
+        for (int u = 0; u < U; ++u)
 #pragma unroll
-            for (int j = 0; j < 3; ++j) { sa = dot_chunk<DT>(ca[u][j], q, j, sa); sb = dot_chunk<DT>(cb[u][j], q, j, sb); }
-            v[u][0] = sa; v[u][1] = sb;
-        }
+            for (int t = 0; t < QT; ++t) {
+                float sa = 0.f, sb = 0.f;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) { sa = dot_chunk<DT>(ca[u][j], q[t], j, sa); sb = dot_chunk<DT>(cb[u][j], q[t], j, sb); }
+                v[u][2 * t] = sa; v[u][2 * t + 1] = sb;
+            }
         // Transposing reduction: each split halves the number of row-steps a lane carries.
         {
             int stride = G / 2;
@@ -117,7 +130,7 @@ gemv_scan_kernel(ScanArgs a) {
 #pragma unroll
                 for (int i = 0; i < half; ++i)
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
+                    for (int c = 0; c < NV; ++c) {
                         float send = upper ? v[i][c] : v[i + half][c];
                         float keep = upper ? v[i + half][c] : v[i][c];
                         v[i][c] = keep + __shfl_xor_sync(kFull, send, stride);
@@ -125,40 +138,49 @@ gemv_scan_kernel(ScanArgs a) {
                 stride >>= 1;
             }
 #pragma unroll
-            for (; stride > 0; stride >>= 1) {
-                v[0][0] += __shfl_xor_sync(kFull, v[0][0], stride);
-                v[0][1] += __shfl_xor_sync(kFull, v[0][1], stride);
-            }
+            for (; stride > 0; stride >>= 1)
+#pragma unroll
+                for (int c = 0; c < NV; ++c) v[0][c] += __shfl_xor_sync(kFull, v[0][c], stride);
         }
-        const float fused = fuse32(v[0][0], v[0][1], fl, w);
-        const uint64_t key = make_key(fused, uint32_t(my_row));
-        top.push(owner && my_row < n && key > top.bound, key, lane);
+#pragma unroll
+        for (int t = 0; t < QT; ++t) {
+            const float fused = fuse32(v[0][2 * t], v[0][2 * t + 1], fl, w[t]);
+            const uint64_t key = make_key(fused, uint32_t(my_row));
+            top[t].push(owner && my_row < n && key > top[t].bound, key, lane);
+        }
     }
 
-    // ---- this warp's best k, then the CTA's best k ---------------------------------------------
-    top.compact(lane);
-    if (lane == 0) s_count[warp] = top.count;
+    // ---- this warp's best k per query, then the CTA's best k --------------------------------------
+#pragma unroll
+    for (int t = 0; t < QT; ++t) {
+        top[t].compact(lane);
+        if (lane == 0) s_count[warp][t] = top[t].count;
+    }
     __syncthreads();
     if (warp == 0) {
-        for (int w2 = 1; w2 < kScanWarps; ++w2) {
-            const int c2 = s_count[w2];
-            for (int i = 0; i < c2; i += 32) {
-                const bool in = i + lane < c2;
-                const uint64_t key = in ? s_keys[w2][i + lane] : 0ull;
-                top.push(in && key > top.bound, key, lane);
+#pragma unroll
+        for (int t = 0; t < QT; ++t) {
+            if (q0 + t >= a.n_queries) break;
+            for (int w2 = 1; w2 < kScanWarps; ++w2) {
+                const int c2 = s_count[w2][t];
+                for (int i = 0; i < c2; i += 32) {
+                    const bool in = i + lane < c2;
+                    const uint64_t key = in ? s_keys[w2][t][i + lane] : 0ull;
+                    top[t].push(in && key > top[t].bound, key, lane);
+                }
             }
+            top[t].compact(lane);
+            const size_t list = size_t(q0 + t) * a.n_partials + blockIdx.x;
+            for (int i = lane; i < a.k; i += 32) a.partial_keys[list * a.k + i] = i < top[t].count ? top[t].buf[i] : 0ull;
         }
-        top.compact(lane);
-        const size_t list = size_t(qi) * a.n_partials + blockIdx.x;
-        for (int i = lane; i < a.k; i += 32) a.partial_keys[list * a.k + i] = i < top.count ? top.buf[i] : 0ull;
     }
 }
 
 // (unroll, blocks/SM) combinations that are instantiated; anything else maps to the nearest.
 static void resolve(const GemvConfig &cfg, int dtype, int *u, int *mb) {
-    // Defaults from the B200 sweep (profiles/r01_gemv_sweep.md): fewer, fatter warps win --
-    // fp32: 1 CTA/SM x 8 warps x 24 LDG.128 per lane (98 KB in flight per SM) = 7.33 TB/s at 10M;
-    // bf16: 2 CTAs/SM x 12 LDG.128 per lane = 7.25 TB/s.
+    // Defaults from the B200 sweep (profiles/r01_gemv_sweep_*.md): fewer, fatter warps win --
+    // fp32: 1 CTA/SM x 8 warps x 24 LDG.128 per lane (98 KB in flight per SM) = 7.5 TB/s at 10M;
+    // bf16: 2 CTAs/SM x 12 LDG.128 per lane = 7.3 TB/s.
     *u = cfg.unroll ? cfg.unroll : (dtype == CAB_BF16 ? 2 : 4);
     *mb = cfg.blocks_per_sm ? cfg.blocks_per_sm : (dtype == CAB_BF16 ? 2 : 1);
     if (*u == 8) *mb = 1;                     // 48 x LDG.128 per lane: 192 registers of loads
@@ -167,28 +189,44 @@ static void resolve(const GemvConfig &cfg, int dtype, int *u, int *mb) {
     if (*mb > 4) *mb = 4;
 }
 
-int gemv_grid_size(const GemvConfig &cfg, int dtype, int sm_count) {
-    int u, mb;
-    resolve(cfg, dtype, &u, &mb);
-    return sm_count * mb;
+GemvPlan plan_gemv(const GemvConfig &cfg, int dtype, int n_queries, int sm_count) {
+    GemvPlan p{};
+    const int qt_max = cfg.query_tile ? cfg.query_tile : (dtype == CAB_BF16 ? 2 : 4);
+    p.qt = n_queries >= 4 && qt_max >= 4 ? 4 : (n_queries >= 2 && qt_max >= 2 ? 2 : 1);
+    if (p.qt == 1) resolve(cfg, dtype, &p.u, &p.mb);
+    else { p.u = 2; p.mb = p.qt == 4 ? 1 : 2; }       // multi-query tiles: 12 loads in flight + QT query register sets
+    p.grid_x = sm_count * p.mb;
+    p.groups = (n_queries + p.qt - 1) / p.qt;
+    return p;
+}
+int gemv_max_grid(int sm_count) { return sm_count * 4; }
+
+template <int DT, int U, int MB, int QT>
+static void launch_one(const ScanArgs &a, dim3 grid, cudaStream_t s) {
+    constexpr size_t smem = sizeof(uint64_t) * kScanWarps * QT * kWarpCap + sizeof(int) * kScanWarps * QT;
+    static bool attr_done = false;
+    if (smem > 48 * 1024 && !attr_done) {
+        cudaFuncSetAttribute(gemv_scan_kernel<DT, U, MB, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        attr_done = true;
+    }
+    gemv_scan_kernel<DT, U, MB, QT><<<grid, kScanThreads, smem, s>>>(a);
 }
 
 template <int DT>
-static void launch_dt(const ScanArgs &a, int u, int mb, dim3 grid, cudaStream_t s) {
-#define CAB_CASE(U_, MB_) if (u == U_ && mb == MB_) { gemv_scan_kernel<DT, U_, MB_><<<grid, kScanThreads, 0, s>>>(a); return; }
+static void launch_dt(const ScanArgs &a, const GemvPlan &p, dim3 grid, cudaStream_t s) {
+    if (p.qt == 4) { if constexpr (DT == CAB_F32) launch_one<DT, 2, 1, 4>(a, grid, s); return; }
+    if (p.qt == 2) { launch_one<DT, 2, 2, 2>(a, grid, s); return; }
+#define CAB_CASE(U_, MB_) if (p.u == U_ && p.mb == MB_) { launch_one<DT, U_, MB_, 1>(a, grid, s); return; }
     CAB_CASE(8, 1) CAB_CASE(4, 1) CAB_CASE(4, 2)
     CAB_CASE(2, 1) CAB_CASE(2, 2) CAB_CASE(2, 3) CAB_CASE(2, 4)
     CAB_CASE(1, 1) CAB_CASE(1, 2) CAB_CASE(1, 3) CAB_CASE(1, 4)
 #undef CAB_CASE
 }
 
-void launch_gemv_scan(const ScanArgs &a, const GemvConfig &cfg, int sm_count, cudaStream_t s) {
-    (void)sm_count;
-    int u, mb;
-    resolve(cfg, a.dtype, &u, &mb);
-    dim3 grid(a.n_partials, a.n_queries);
-    if (a.dtype == CAB_BF16) launch_dt<CAB_BF16>(a, u, mb, grid, s);
-    else launch_dt<CAB_F32>(a, u, mb, grid, s);
+void launch_gemv_scan(const ScanArgs &a, const GemvPlan &p, cudaStream_t s) {
+    dim3 grid(p.grid_x, p.groups);
+    if (a.dtype == CAB_BF16) launch_dt<CAB_BF16>(a, p, grid, s);
+    else launch_dt<CAB_F32>(a, p, grid, s);
 }
 
 }  // namespace cab

@@ -49,13 +49,20 @@ struct ScanArgs {
     unsigned int *work_counters;   // GEMV: [n_queries] chunk tickets, zero on entry (finalize resets them)
 };
 struct GemvConfig {
-    int variant;               // 0 = LDG register pipeline, 1 = bulk-copy smem ring
+    int variant;               // 0 = LDG register pipeline (the only one built)
     int blocks_per_sm;         // 0 = default
     int unroll;                // 0 = default
+    int query_tile;            // max queries scored per corpus pass: 0 = default (fp32 4, bf16 2), 1, 2, 4
 };
-// Number of partial lists (grid size) the GEMV scan will use for this config.
-int gemv_grid_size(const GemvConfig &cfg, int dtype, int sm_count);
-void launch_gemv_scan(const ScanArgs &a, const GemvConfig &cfg, int sm_count, cudaStream_t s);
+// How one GEMV launch over `n_queries` queries is shaped.
+struct GemvPlan {
+    int u, mb, qt;             // row-steps in flight, CTAs per SM, queries per pass
+    int grid_x;                // CTAs per query group == partial lists per query
+    int groups;                // ceil(n_queries / qt)
+};
+GemvPlan plan_gemv(const GemvConfig &cfg, int dtype, int n_queries, int sm_count);
+int gemv_max_grid(int sm_count);       // upper bound of grid_x over all plans (buffer sizing)
+void launch_gemv_scan(const ScanArgs &a, const GemvPlan &plan, cudaStream_t s);
 
 // ---- tensor-core scan (cab_gemm_tc.cu) -----------------------------------------------------------
 constexpr int kGemmListCap = 256;       // slots per (CTA pair, query) candidate list

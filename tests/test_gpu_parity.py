@@ -142,13 +142,33 @@ def test_scan_variants_agree():
     idx.append_synth(seed, n, 0, n, n_queries=2, plants=40, partial=True)
     q = synth.raw_queries(seed, 0, 2)
     base = None
-    for unroll, bps in ((4, 2), (4, 1), (2, 3), (2, 2), (1, 4), (1, 2)):
+    idx.set_option("gemv_query_tile", 1)              # one query per pass: exercises the (U, MB) variants
+    for unroll, bps in ((8, 1), (4, 2), (4, 1), (2, 3), (2, 2), (1, 4), (1, 2)):
         idx.set_option("gemv_unroll", unroll)
         idx.set_option("gemv_blocks_per_sm", bps)
         res = idx.search(q, [0.5, 0.3], [0.5, 0.7], k=50)
         key = (res.indices.tolist(), res.fusion.tolist(), res.count.tolist())
         base = base or key
         assert key == base
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_query_tiles_agree(dtype):
+    """Scoring 1, 2 or 4 queries per corpus pass (register tiling) gives bit-identical results,
+    also for batches that do not fill the last tile."""
+    seed, n, nq = 78, 50000, 7
+    idx = SegmentIndex(dtype)
+    idx.append_synth(seed, n, 0, n, n_queries=nq, plants=40, partial=True)
+    q = synth.raw_queries(seed, 0, nq)
+    wa = np.linspace(0.2, 0.8, nq); wb = 1.0 - wa
+    base = None
+    for tile in (1, 2, 4, 0):
+        idx.set_option("gemv_query_tile", tile)
+        for k, thr in ((10, 0.1), (100, -1.0)):
+            res = idx.search(q, wa, wb, k=k, threshold=thr, path="gemv")
+            key = (res.indices.tolist(), res.fusion.tolist(), res.asr_sim.tolist(), res.count.tolist())
+            base = base or {}
+            assert base.setdefault((k, thr), key) == key, (dtype, tile, k)
 
 
 def test_finalize_paths_agree():
