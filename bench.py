@@ -229,7 +229,20 @@ def main():
     wa_all = np.array([w_classes[i % len(w_classes)] for i in range(n_steps * nq)])
     wb_all = 1.0 - wa_all
     q_dev = torch.from_numpy(q_host).cuda()
-    sharded = ShardedSearcher(idx, rank, world, exchange=args.exchange, max_queries=max(nq, 1), max_k=k)
+    exchange = args.exchange
+    try:
+        sharded = ShardedSearcher(idx, rank, world, exchange=exchange, max_queries=max(nq, 1), max_k=k)
+        ok = 1
+    except Exception as e:          # e.g. CUDA IPC not permitted in this container: use the NCCL all-gather
+        ok = 0
+        if rank == 0:
+            print(f"bench: peer-memory exchange unavailable ({e}); using NCCL all-gather", file=sys.stderr)
+    if world > 1:
+        t_ok = torch.tensor([ok], device="cuda")
+        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+        if int(t_ok.item()) == 0:
+            exchange = "nccl"
+            sharded = ShardedSearcher(idx, rank, world, exchange="nccl")
 
     def step_device(i):
         sl = slice(i * nq, (i + 1) * nq)
@@ -329,7 +342,7 @@ def main():
                        "l2": "inputs larger than L2 (corpus bytes per GPU >> 126 MB)",
                        "exchange": "none" if world == 1 else (
                            "per-shard top-k (24 B x k x Q per rank) stored into every rank's buffer over NVLink peer memory "
-                           "inside the finalize kernel + flag wait in the merge kernel" if args.exchange == "p2p" else
+                           "inside the finalize kernel + flag wait in the merge kernel" if exchange == "p2p" else
                            "NCCL all_gather of per-shard top-k (24 B x k x Q per rank) + device merge"),
                        "value_definition": "queries/s x global_segments/1e6"},
             "queries_per_s": nq * 1e3 / ms_step, "hbm_gbs_all_gpus": world * alg_bytes * nq / (ms_step * 1e-3) / 1e9,

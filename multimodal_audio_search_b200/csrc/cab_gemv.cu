@@ -191,7 +191,8 @@ static void resolve(const GemvConfig &cfg, int dtype, int *u, int *mb) {
 
 GemvPlan plan_gemv(const GemvConfig &cfg, int dtype, int n_queries, int sm_count) {
     GemvPlan p{};
-    const int qt_max = cfg.query_tile ? cfg.query_tile : (dtype == CAB_BF16 ? 2 : 4);
+    int qt_max = cfg.query_tile ? cfg.query_tile : 4;
+    if (dtype == CAB_BF16 && qt_max > 2) qt_max = 2;       // bf16 keeps 24 query registers per query: tiles of 2
     p.qt = n_queries >= 4 && qt_max >= 4 ? 4 : (n_queries >= 2 && qt_max >= 2 ? 2 : 1);
     if (p.qt == 1) resolve(cfg, dtype, &p.u, &p.mb);
     else { p.u = 2; p.mb = p.qt == 4 ? 1 : 2; }       // multi-query tiles: 12 loads in flight + QT query register sets
