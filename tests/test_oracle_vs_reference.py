@@ -40,3 +40,30 @@ def test_weights_property():
         s = s.upper() if upper else s
         assert no.analyze_query_for_weights(s) == rs.reference_weights(s)
     run()
+
+
+def test_accelerate_accepts_the_real_reference_object():
+    """`accelerate()` on an actual reference DualPipelineAudioSearch instance: the patched method
+    uses the reference's own attributes (audio_segments, text_embedder, stats,
+    _analyze_query_for_weights).  Without a GPU it must return ([], {}) for an empty library and
+    raise -- never compute -- for a populated one."""
+    from multimodal_audio_search_b200 import _native as N
+    from multimodal_audio_search_b200 import accelerate
+    a, b, f, _ = synth.library(5, 12, 1, 4)
+    q = synth.raw_queries(5, 0, 1)
+    eng = rs.reference_engine([], {"zzz": q[0]})
+    original = type(eng).search_with_fusion
+    accelerate(eng)
+    assert eng.search_with_fusion.__func__ is not original
+    assert eng.search_with_fusion("zzz") == ([], {})
+    assert eng.stats["search_pipeline"].total_calls == 0
+    eng.audio_segments.extend(rs.segments_from_arrays(a, b, f))
+    if N.lib().cab_device_count() == 0:
+        with pytest.raises(N.CabError):
+            eng.search_with_fusion("zzz")
+    else:                                            # on a GPU box: same answer as the reference
+        ref = rs.reference_engine(rs.segments_from_arrays(a, b, f), {"zzz": q[0]})
+        want, _ = ref.search_with_fusion("zzz")
+        got, info = eng.search_with_fusion("zzz")
+        assert [r["segment_id"] for r in got] == [r["segment_id"] for r in want]
+        assert info["analysis"] == "Balanced (no specific keywords detected)"
