@@ -393,6 +393,41 @@ __global__ void __launch_bounds__(kEmitThreads) emit_kernel(EmitArgs a) {
         }
         s_score[t] = sc; s_index[t] = gi; s_pos[t] = uint16_t(t);
     }
+    if (n_cand <= kEmitThreads) {
+        // Few candidates (e.g. 8 shards x top-10): rank by counting instead of sorting -- no barriers.
+        __syncthreads();
+        const int t = threadIdx.x;
+        int rank = 0, n_res = 0;
+        const uint64_t sc = t < n_cand ? s_score[t] : 0ull;
+        const int64_t gi = t < n_cand ? s_index[t] : INT64_MAX;
+        for (int j = 0; j < n_cand; ++j) {
+            const uint64_t sj = s_score[j];
+            n_res += sj != 0ull;
+            rank += (sj > sc) || (sj == sc && sj != 0ull && s_index[j] < gi);
+        }
+        const size_t o0 = size_t(qi) * a.k;
+        if (sc != 0ull && rank < a.k) {
+            const cab_candidate c = *cand_at(t);
+            a.out_index[o0 + rank] = c.index;
+            a.out_fusion[o0 + rank] = unorderable64(sc);
+            a.out_asr[o0 + rank] = c.asr_sim;
+            a.out_audio[o0 + rank] = c.audio_sim;
+            a.out_flags[o0 + rank] = uint8_t(c.flags);
+        }
+        const int n_out = n_res < a.k ? n_res : a.k;
+        for (int i = n_out + t; i < a.k; i += kEmitThreads) {
+            a.out_index[o0 + i] = -1;
+            a.out_fusion[o0 + i] = 0.0;
+            a.out_asr[o0 + i] = 0.f;
+            a.out_audio[o0 + i] = 0.f;
+            a.out_flags[o0 + i] = 0;
+        }
+        if (t == 0) {
+            a.out_count[qi] = n_out;
+            if (qi == 0 && a.nonfinite_out) { *a.nonfinite_out = *a.nonfinite; }
+        }
+        return;
+    }
     block_sort_results(s_score, s_index, s_pos, np2);
     for (int i = threadIdx.x; i < a.k; i += kEmitThreads) {
         const size_t o = size_t(qi) * a.k + i;

@@ -255,9 +255,10 @@ def test_device_calls_are_ordered_on_the_callers_stream():
     np.testing.assert_array_equal(got, host_gemv.indices)
 
 
-def test_sharded_merge_equals_single_index():
+@pytest.mark.parametrize("k", [10, 100])
+def test_sharded_merge_equals_single_index(k):
     torch = pytest.importorskip("torch")
-    seed, n, k = 321, 30000, 100
+    seed, n = 321, 30000
     whole = SegmentIndex("fp32")
     whole.append_synth(seed, n, 0, n, n_queries=2, plants=80, partial=True)
     q = synth.raw_queries(seed, 0, 2)
