@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -66,6 +67,8 @@ struct cab_index {
     uint32_t peer_epoch = 0;
     unsigned int *d_done = nullptr;
     int *d_status = nullptr;
+    unsigned int *d_host_done = nullptr;             // CTA counter for host-visible completion
+    uint32_t host_epoch = 0;
     int64_t launches = 0;
     std::string err;
     int sticky = CAB_OK;
@@ -167,6 +170,8 @@ int cab_index_create(int dim, int dtype, int64_t capacity_rows, int device, cab_
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&idx->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&idx->d_nonfinite, sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(idx->d_nonfinite, 0, sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&idx->d_host_done, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(idx->d_host_done, 0, sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMalloc(&idx->d_counters, 64 * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(idx->d_counters, 0, 64 * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&idx->ev_in, cudaEventDisableTiming);
@@ -195,7 +200,7 @@ int cab_index_destroy(cab_index *idx) {
     cudaFree(idx->d_out); cudaFree(idx->d_gemm_ws); cudaFree(idx->d_nonfinite); cudaFree(idx->d_rows); cudaFree(idx->d_counters);
     for (int r = 0; r < idx->peer_world; ++r)
         if (idx->peer_attached && r != idx->peer_rank && idx->peer_ptr[r]) cudaIpcCloseMemHandle(idx->peer_ptr[r]);
-    cudaFree(idx->d_peer); cudaFree(idx->d_done); cudaFree(idx->d_status);
+    cudaFree(idx->d_peer); cudaFree(idx->d_done); cudaFree(idx->d_status); cudaFree(idx->d_host_done);
     cudaFreeHost(idx->h_in); cudaFreeHost(idx->h_out); cudaFreeHost(idx->h_rows);
     if (idx->ev_in) cudaEventDestroy(idx->ev_in);
     if (idx->ev_t0) cudaEventDestroy(idx->ev_t0);
@@ -527,7 +532,7 @@ int cab_index_load(const char *path, int device, int64_t r0, int64_t r1, cab_ind
 
 // ---- search ------------------------------------------------------------------------------------
 struct OutLayout {
-    size_t index, fusion, asr, audio, flags, count, nonfinite, total;
+    size_t index, fusion, asr, audio, flags, count, nonfinite, done, total;
 };
 static OutLayout out_layout(int nq, int k) {
     OutLayout L;
@@ -538,7 +543,8 @@ static OutLayout out_layout(int nq, int k) {
     L.audio = o; o += align_up(size_t(nq) * k * 4, 256);
     L.flags = o; o += align_up(size_t(nq) * k, 256);
     L.count = o; o += align_up(size_t(nq) * 4, 256);
-    L.nonfinite = o; o += 256;
+    L.nonfinite = o; o += 128;
+    L.done = o; o += 128;
     L.total = o;
     return L;
 }
@@ -563,25 +569,38 @@ static int ensure_workspace(cab_index *idx, int nq, int k, int n_partials, int s
     return CAB_OK;
 }
 
-// Resolve output pointers for the emit stage (user device pointers, or the packed internal block).
-static EmitArgs make_emit(cab_index *idx, int n_lists, int nq, int k, double threshold,
-                          int64_t *out_index, double *out_fusion, float *out_asr, float *out_audio,
-                          uint8_t *out_flags, int32_t *out_count, int out_loc) {
+// Resolve output pointers for the emit stage: user device pointers; or, for host results, the
+// handle's MAPPED PINNED host block (the kernel writes the results straight into host memory over
+// PCIe and raises a completion flag there -- no D2H copy, no stream synchronisation); device
+// scratch for outputs the caller did not ask for.
+static int make_emit(cab_index *idx, int n_lists, int nq, int k, double threshold,
+                     int64_t *out_index, double *out_fusion, float *out_asr, float *out_audio,
+                     uint8_t *out_flags, int32_t *out_count, int out_loc, EmitArgs *out) {
     const OutLayout L = out_layout(nq, k);
-    uint8_t *d = idx->d_out;
     EmitArgs ea{};
     ea.n_lists = n_lists; ea.n_queries = nq; ea.k = k;
     ea.w_asr = idx->d_w64; ea.w_audio = idx->d_w64 + nq; ea.threshold = threshold;
+    ea.nonfinite = idx->d_nonfinite;
     const bool dev = out_loc == CAB_DEVICE;
+    uint8_t *d = idx->d_out;
+    if (!dev) {
+        int rc = ensure_pinned(idx, &idx->h_out, &idx->h_out_bytes, L.total);
+        if (rc != CAB_OK) return rc;
+        d = idx->h_out;                                   // UVA: pinned host memory is device-addressable
+        ea.done_flag = reinterpret_cast<uint32_t *>(d + L.done);
+        ea.done_epoch = ++idx->host_epoch ? idx->host_epoch : ++idx->host_epoch;
+        ea.done_counter = idx->d_host_done;
+        *reinterpret_cast<volatile uint32_t *>(d + L.done) = 0u;
+    }
     ea.out_index = dev && out_index ? out_index : reinterpret_cast<int64_t *>(d + L.index);
     ea.out_fusion = dev && out_fusion ? out_fusion : reinterpret_cast<double *>(d + L.fusion);
     ea.out_asr = dev && out_asr ? out_asr : reinterpret_cast<float *>(d + L.asr);
     ea.out_audio = dev && out_audio ? out_audio : reinterpret_cast<float *>(d + L.audio);
     ea.out_flags = dev && out_flags ? out_flags : d + L.flags;
     ea.out_count = dev && out_count ? out_count : reinterpret_cast<int32_t *>(d + L.count);
-    ea.nonfinite = idx->d_nonfinite;
     ea.nonfinite_out = reinterpret_cast<int *>(d + L.nonfinite);
-    return ea;
+    *out = ea;
+    return CAB_OK;
 }
 
 // One H2D copy of the per-search parameter block (weights, and the queries if they are on the host).
@@ -647,8 +666,8 @@ static int run_local(cab_index *idx, const float *queries, int queries_loc, cons
     if ((rc = stage_params(idx, queries, queries_loc, w_asr, w_audio, nq, s, &dq))) return rc;
 
     EmitArgs ea{};
-    if (out) ea = make_emit(idx, 1, nq, k, threshold, out->index, out->fusion, out->asr, out->audio,
-                            out->flags, out->count, out->loc);
+    if (out && (rc = make_emit(idx, 1, nq, k, threshold, out->index, out->fusion, out->asr, out->audio,
+                               out->flags, out->count, out->loc, &ea))) return rc;
     idx->timed = false;
     cab_candidate *cands = cand_dst ? cand_dst : idx->d_cands;      // sharded search: straight into the caller's block
     if (idx->size == 0) {
@@ -697,7 +716,7 @@ static int run_local(cab_index *idx, const float *queries, int queries_loc, cons
             eb.out_index = ea.out_index + size_t(q0) * k; eb.out_fusion = ea.out_fusion + size_t(q0) * k;
             eb.out_asr = ea.out_asr + size_t(q0) * k; eb.out_audio = ea.out_audio + size_t(q0) * k;
             eb.out_flags = ea.out_flags + size_t(q0) * k; eb.out_count = ea.out_count + q0;
-            if (q0 + batch < nq) eb.nonfinite_out = nullptr;    // only the last batch reports the flag
+            if (q0 + batch < nq) { eb.nonfinite_out = nullptr; eb.done_epoch = 0; }   // only the last batch reports / signals
             launch_finalize(fa, &eb, s);
         } else {
             launch_finalize(fa, nullptr, s);
@@ -709,20 +728,32 @@ static int run_local(cab_index *idx, const float *queries, int queries_loc, cons
     return CAB_OK;
 }
 
-// Bring the packed output block back to the host (or nothing to do for device outputs).
+// Host results: wait for the kernel's completion flag in the mapped pinned block, then hand the
+// values to the caller's arrays (nothing to do for device outputs).
 static int finish_outputs(cab_index *idx, int nq, int k, const UserOut &o, cudaStream_t s) {
     if (o.loc == CAB_DEVICE) {
         if (idx->opt_sync) CU(idx, cudaStreamSynchronize(s));
         return CAB_OK;
     }
     const OutLayout L = out_layout(nq, k);
-    int rc = ensure_pinned(idx, &idx->h_out, &idx->h_out_bytes, L.total);
-    if (rc != CAB_OK) return rc;
-    CU(idx, cudaMemcpyAsync(idx->h_out, idx->d_out, L.total, cudaMemcpyDeviceToHost, s));
-    CU(idx, cudaStreamSynchronize(s));
-    idx->ev_in_pending = false;
     const uint8_t *h = idx->h_out;
-    if (*reinterpret_cast<const int *>(h + L.nonfinite)) {
+    const volatile uint32_t *flag = reinterpret_cast<const volatile uint32_t *>(h + L.done);
+    const uint32_t want = idx->host_epoch;
+    bool seen = false;
+    for (long spins = 0; spins < 400000000L; ++spins) {               // bounded: falls back to a stream sync
+        if (*flag == want) { seen = true; break; }
+        if ((spins & 0xFFF) == 0xFFF && cudaStreamQuery(s) != cudaErrorNotReady) break;   // finished or failed
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    if (!seen) {
+        CU(idx, cudaStreamSynchronize(s));
+        if (*flag != want) return fail(idx, CAB_ERR_CUDA, "search finished without raising its completion flag");
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    idx->ev_in_pending = false;
+    if (*reinterpret_cast<const volatile int *>(h + L.nonfinite)) {
         CU(idx, cudaMemsetAsync(idx->d_nonfinite, 0, sizeof(int), s));
         CU(idx, cudaStreamSynchronize(s));
         return fail(idx, CAB_ERR_NONFINITE, "Input contains NaN or infinity (query)");
@@ -779,8 +810,9 @@ int cab_merge_candidates(cab_index *idx, const cab_candidate *cands_device, int 
     if (rc != CAB_OK) return rc;
     if (w_asr && (rc = stage_params(idx, nullptr, CAB_DEVICE, w_asr, w_audio, n_queries, s, nullptr))) return rc;
     const UserOut o{out_index, out_fusion, out_asr, out_audio, out_flags, out_count, out_loc};
-    EmitArgs ea = make_emit(idx, n_lists, n_queries, k, threshold, out_index, out_fusion, out_asr,
-                            out_audio, out_flags, out_count, out_loc);
+    EmitArgs ea{};
+    if ((rc = make_emit(idx, n_lists, n_queries, k, threshold, out_index, out_fusion, out_asr,
+                        out_audio, out_flags, out_count, out_loc, &ea))) return rc;
     ea.cands = cands_device;
     launch_emit(ea, s);
     idx->launches += 1;
@@ -855,8 +887,9 @@ int cab_search_sharded(cab_index *idx, const float *queries, int queries_loc, co
     if (rc != CAB_OK) return rc;
     const UserOut o{out_index, out_fusion, out_asr, out_audio, out_flags, out_count, out_loc};
     if (out_loc != CAB_HOST && out_loc != CAB_DEVICE) return fail(idx, CAB_ERR_INVALID, "out_loc");
-    EmitArgs ea = make_emit(idx, idx->peer_world, n_queries, k, threshold, out_index, out_fusion, out_asr,
-                            out_audio, out_flags, out_count, out_loc);
+    EmitArgs ea{};
+    if ((rc = make_emit(idx, idx->peer_world, n_queries, k, threshold, out_index, out_fusion, out_asr,
+                        out_audio, out_flags, out_count, out_loc, &ea))) return rc;
     ea.cands = pp.bufs[idx->peer_rank];
     ea.wait_flags = pp.flags[idx->peer_rank] + pp.parity * idx->peer_world;
     ea.wait_epoch = epoch;

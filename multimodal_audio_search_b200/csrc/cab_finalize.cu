@@ -95,6 +95,22 @@ __device__ __forceinline__ void peer_signal(const PeerPush &p) {
     }
 }
 
+// Host-visible completion of a launch whose outputs live in mapped pinned host memory: called by
+// all threads of every CTA after their output stores.
+__device__ __forceinline__ void host_signal(const EmitArgs &e) {
+    if (!e.done_flag) return;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && e.done_epoch) {
+        const unsigned prev = atomicAdd(e.done_counter, 1u);
+        if (prev == gridDim.x - 1) {
+            *e.done_counter = 0u;
+            __threadfence_system();
+            st_release_sys(e.done_flag, e.done_epoch);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) peer_push_kernel(const cab_candidate *__restrict__ local, int n_queries, int k, PeerPush p) {
     const int total = n_queries * k;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
@@ -339,6 +355,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, E
             if (qi == 0 && e.nonfinite_out) *e.nonfinite_out = *e.nonfinite;
         }
     }
+    host_signal(e);
 }
 
 void launch_finalize(const FinalizeArgs &a, const EmitArgs *fused_emit, cudaStream_t s) {
@@ -426,6 +443,7 @@ __global__ void __launch_bounds__(kEmitThreads) emit_kernel(EmitArgs a) {
             a.out_count[qi] = n_out;
             if (qi == 0 && a.nonfinite_out) { *a.nonfinite_out = *a.nonfinite; }
         }
+        host_signal(a);
         return;
     }
     block_sort_results(s_score, s_index, s_pos, np2);
@@ -452,6 +470,7 @@ __global__ void __launch_bounds__(kEmitThreads) emit_kernel(EmitArgs a) {
         a.out_count[qi] = s_n;
         if (qi == 0 && a.nonfinite_out) { *a.nonfinite_out = *a.nonfinite; }
     }
+    host_signal(a);
 }
 
 void launch_emit(const EmitArgs &a, cudaStream_t s) {

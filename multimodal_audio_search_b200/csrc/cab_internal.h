@@ -124,6 +124,11 @@ struct EmitArgs {
     int32_t *out_count;
     const int *nonfinite;         // device flag set by scan / ingest kernels
     int *nonfinite_out;           // copy of it next to the outputs (may be null)
+    // zero-copy host results: outputs point into mapped pinned host memory; when every CTA of the
+    // (last) launch has written, done_flag (also in that block) is set to done_epoch for the host
+    uint32_t *done_flag;          // null = outputs are ordinary device memory
+    uint32_t done_epoch;
+    unsigned int *done_counter;   // device scratch, zero between launches
     // peer exchange: wait until wait_flags[0..n_lists) all hold wait_epoch before reading cands
     const uint32_t *wait_flags;   // null = no wait
     uint32_t wait_epoch;

@@ -181,9 +181,16 @@ class SegmentIndex:
     # -- search --------------------------------------------------------------------------------
     @staticmethod
     def _weights(w_asr, w_audio, nq):
-        wa = np.array(np.broadcast_to(np.asarray(w_asr, dtype=np.float64), (nq,)), dtype=np.float64)   # owned copies
-        wb = np.array(np.broadcast_to(np.asarray(w_audio, dtype=np.float64), (nq,)), dtype=np.float64)
-        return wa, wb
+        """Owned float64 [nq] arrays (scalars broadcast)."""
+        wa = np.asarray(w_asr, dtype=np.float64).reshape(-1)
+        wb = np.asarray(w_audio, dtype=np.float64).reshape(-1)
+        if wa.size != nq:
+            wa = np.full(nq, wa[0]) if wa.size == 1 else wa
+        if wb.size != nq:
+            wb = np.full(nq, wb[0]) if wb.size == 1 else wb
+        if wa.size != nq or wb.size != nq:
+            raise ValueError("one weight per query (or a scalar) expected")
+        return np.ascontiguousarray(wa), np.ascontiguousarray(wb)
 
     def search(self, queries, w_asr=0.5, w_audio=0.5, k: int = 10, threshold: float = 0.1,
                path: str = "auto") -> SearchResult:
@@ -191,17 +198,24 @@ class SegmentIndex:
         the call); CUDA torch queries -> CUDA torch results on torch's current stream."""
         if _is_torch_cuda(queries):
             return self._search_device(queries, w_asr, w_audio, k, threshold, path)
-        q = _np_f32(np.atleast_2d(queries), self.dim)
+        q = queries
+        if not (isinstance(q, np.ndarray) and q.dtype == np.float32 and q.flags.c_contiguous):
+            q = np.ascontiguousarray(q, dtype=np.float32)
+        if q.ndim == 1:
+            q = q.reshape(1, -1)
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise ValueError(f"expected [n x {self.dim}] float32 queries, got shape {q.shape}")
         nq = q.shape[0]
         wa, wb = self._weights(w_asr, w_audio, nq)
-        out = SearchResult(np.empty((nq, k), np.int64), np.empty((nq, k), np.float64),
-                           np.empty((nq, k), np.float32), np.empty((nq, k), np.float32),
-                           np.empty((nq, k), np.uint8), np.empty((nq,), np.int32))
-        N.check(self._lib.cab_search(self._h, _ptr(q), N.CAB_HOST, _ptr(wa), _ptr(wb), nq, k,
-                                     float(threshold), _PATHS[path], _ptr(out.indices), _ptr(out.fusion),
-                                     _ptr(out.asr_sim), _ptr(out.audio_sim), _ptr(out.flags),
-                                     _ptr(out.count), N.CAB_HOST, None), self._h)
-        return out
+        oi, of = np.empty((nq, k), np.int64), np.empty((nq, k), np.float64)
+        oa, ob = np.empty((nq, k), np.float32), np.empty((nq, k), np.float32)
+        ofl, oc = np.empty((nq, k), np.uint8), np.empty((nq,), np.int32)
+        rc = self._lib.cab_search(self._h, q.ctypes.data, N.CAB_HOST, wa.ctypes.data, wb.ctypes.data, nq, k,
+                                  threshold, _PATHS[path], oi.ctypes.data, of.ctypes.data, oa.ctypes.data,
+                                  ob.ctypes.data, ofl.ctypes.data, oc.ctypes.data, N.CAB_HOST, None)
+        if rc:
+            N.check(rc, self._h)
+        return SearchResult(oi, of, oa, ob, ofl, oc)
 
     def _search_device(self, queries, w_asr, w_audio, k, threshold, path) -> SearchResult:
         """CUDA tensors in, CUDA tensors out, through the PyTorch extension (torch.ops.cab.search)."""
