@@ -84,7 +84,7 @@ gemv_scan_kernel(ScanArgs a) {
     // chunk comes from a per-group atomic counter, fetched one chunk ahead so the atomic's latency
     // is hidden.  Unlike a static split this tolerates SMs that are late or busy (another kernel,
     // e.g. an NCCL collective, holding an SM) and evens out SM-to-SM speed differences.
-    constexpr int kChunkRows = kRowsPerIter * (64 / kRowsPerIter);      // 64 rows per chunk
+    const int kChunkRows = a.chunk_rows >= kRowsPerIter ? (a.chunk_rows / kRowsPerIter) * kRowsPerIter : kRowsPerIter;
     const int64_t n_chunks = (n + kChunkRows - 1) / kChunkRows;
     unsigned int *counter = a.work_counters + blockIdx.y;
     int64_t chunk = gwarp;

@@ -47,6 +47,7 @@ struct ScanArgs {
     int n_partials;            // == grid size of the scan (GEMV) / number of CTA pairs (GEMM)
     int *nonfinite;            // set if a query holds NaN/Inf
     unsigned int *work_counters;   // GEMV: [n_queries] chunk tickets, zero on entry (finalize resets them)
+    int chunk_rows;                // GEMV: rows per dynamically scheduled chunk
 };
 struct GemvConfig {
     int variant;               // 0 = LDG register pipeline (the only one built)
