@@ -58,6 +58,7 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
         "sm__cycles_elapsed.avg", "smsp__cycles_active.avg"]
 traffic = {}
+REPORT_WORKLOAD = {"prof_gemv": "1m_fp32_q1_top10", "prof_gemm": "10m_bf16_q256_top100"}
 for rep in sorted(f for f in os.listdir(OUT) if f.endswith(".ncu-rep")):
     r = subprocess.run(["ncu", "-i", os.path.join(OUT, rep), "--page", "raw", "--csv"], capture_output=True, text=True)
     rows = list(csv.reader(io.StringIO(r.stdout)))
@@ -65,8 +66,9 @@ for rep in sorted(f for f in os.listdir(OUT) if f.endswith(".ncu-rep")):
         continue
     H, U = rows[0], rows[1]
     name = rep.replace(".ncu-rep", "")
-    with open(os.path.join(PROF, f"{tag}_{name}_{workload}.md"), "w") as f:
-        f.write(f"# ncu --set full --clock-control none: {name} ({workload}), {tag}\n\n")
+    wl = REPORT_WORKLOAD.get(name, workload)
+    with open(os.path.join(PROF, f"{tag}_{name}_{wl}.md"), "w") as f:
+        f.write(f"# ncu --set full --clock-control none: {name} ({wl}), {tag}\n\n")
         for r_ in rows[2:]:
             kn = r_[H.index("Kernel Name")]
             f.write(f"## `{kn}`\n\n| metric | value | unit |\n|---|---:|---|\n")
@@ -79,16 +81,16 @@ for rep in sorted(f for f in os.listdir(OUT) if f.endswith(".ncu-rep")):
                 wr = float(r_[H.index("dram__bytes_write.sum")].replace(",", ""))
                 scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}
                 tb = rd * scale[U[H.index("dram__bytes_read.sum")]] + wr * scale[U[H.index("dram__bytes_write.sum")]]
-                traffic.setdefault(kn.split("(")[0], []).append(tb)
+                traffic.setdefault((wl, kn.split("(")[0]), []).append(tb)
             except Exception:
                 pass
     print("wrote", name)
 if traffic:
     tp = os.path.join(PROF, "traffic.json")
     t = json.load(open(tp)) if os.path.exists(tp) else {}
-    main_k = max(traffic, key=lambda k: sum(traffic[k]))
-    t[workload] = sum(traffic[main_k]) / len(traffic[main_k])
-    t[workload + "_kernel"] = main_k
+    for (wl, kern), vals in traffic.items():
+        t[wl] = sum(vals) / len(vals)
+        t[wl + "_kernel"] = kern
     json.dump(t, open(tp, "w"), indent=1)
     print("traffic", t)
 
