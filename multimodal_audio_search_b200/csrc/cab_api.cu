@@ -58,7 +58,7 @@ struct cab_index {
     // options
     GemvConfig gemv{0, 0, 0, 0};
     int64_t opt_time_kernels = 0, opt_sync = 0, opt_gemm_min_queries = 64, opt_gemv_batch = 32;
-    int64_t opt_finalize_general = 0, opt_chunk_rows = 32;   // chunk sweep: profiles/r01_gemv_chunk_sweep.md
+    int64_t opt_finalize_general = 0, opt_chunk_rows = 0;    // 0 = auto: 96 KB of corpus per chunk (fp32 32 rows, bf16 64), profiles/r01_gemv_chunk_sweep.md
     // peer-memory exchange (sharded search)
     int peer_world = 0, peer_rank = 0, peer_qcap = 0, peer_kcap = 0;
     bool peer_attached = false;
@@ -683,7 +683,7 @@ static int run_local(cab_index *idx, const float *queries, int queries_loc, cons
     sa.dtype = idx->dtype; sa.k = k;
     sa.select_threshold = float(threshold) - 1e-6f;
     sa.partial_keys = idx->d_partial_keys;
-    sa.n_partials = n_partials; sa.nonfinite = idx->d_nonfinite; sa.work_counters = idx->d_counters; sa.chunk_rows = int(idx->opt_chunk_rows);
+    sa.n_partials = n_partials; sa.nonfinite = idx->d_nonfinite; sa.work_counters = idx->d_counters; sa.chunk_rows = idx->opt_chunk_rows ? int(idx->opt_chunk_rows) : (idx->dtype == CAB_BF16 ? 64 : 32);
     FinalizeArgs fa{};
     fa.asr = idx->asr; fa.audio = idx->audio; fa.flags = idx->flags; fa.dtype = idx->dtype;
     fa.row_base = idx->row_base; fa.k = k; fa.partial_keys = idx->d_partial_keys;
@@ -911,7 +911,7 @@ int cab_index_set_option(cab_index *idx, const char *key, int64_t value) {
     else if (k == "time_kernels") idx->opt_time_kernels = value != 0;
     else if (k == "sync_after_search") idx->opt_sync = value != 0;
     else if (k == "finalize_general") idx->opt_finalize_general = value != 0;
-    else if (k == "gemv_chunk_rows") { if (value < 1 || value > 4096) return fail(idx, CAB_ERR_INVALID, "gemv_chunk_rows in 1..4096"); idx->opt_chunk_rows = value; }
+    else if (k == "gemv_chunk_rows") { if (value < 0 || value > 4096) return fail(idx, CAB_ERR_INVALID, "gemv_chunk_rows in 0..4096 (0 = auto)"); idx->opt_chunk_rows = value; }
     else if (k == "gemm_min_queries") { if (value < 1) return fail(idx, CAB_ERR_INVALID, "gemm_min_queries >= 1"); idx->opt_gemm_min_queries = value; }
     else if (k == "gemv_batch") { if (value < 1 || value > 64) return fail(idx, CAB_ERR_INVALID, "gemv_batch in 1..64"); idx->opt_gemv_batch = value; }
     else return fail(idx, CAB_ERR_INVALID, "unknown option '%s'", key);

@@ -112,9 +112,14 @@ struct WarpTopK {
         buf = smem; k = k_; floor_ = floor_key; bound = floor_key; count = 0;
     }
     // Sort, keep the best k, tighten the bound.  Leaves buf[0..count) sorted descending.
+    // The sort network is sized to the fill (64 / 128 / 256 keys): at the end of a scan most
+    // buffers hold a handful of keys, and a 64-key sort is ~6x cheaper than the full one.
     __device__ __noinline__ void compact(int lane) {
-        for (int i = count + lane; i < kWarpCap; i += 32) buf[i] = 0ull;
-        warp_sort_desc<kWarpCap>(buf, lane);
+        const int n = count <= 64 ? 64 : (count <= 128 ? 128 : kWarpCap);
+        for (int i = count + lane; i < n; i += 32) buf[i] = 0ull;
+        if (n == 64) warp_sort_desc<64>(buf, lane);
+        else if (n == 128) warp_sort_desc<128>(buf, lane);
+        else warp_sort_desc<kWarpCap>(buf, lane);
         if (count > k) count = k;
         if (count == k) bound = buf[k - 1] > floor_ ? buf[k - 1] : floor_;
         __syncwarp();

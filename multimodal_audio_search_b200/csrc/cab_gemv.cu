@@ -84,8 +84,17 @@ gemv_scan_kernel(ScanArgs a) {
     // chunk comes from a per-group atomic counter, fetched one chunk ahead so the atomic's latency
     // is hidden.  Unlike a static split this tolerates SMs that are late or busy (another kernel,
     // e.g. an NCCL collective, holding an SM) and evens out SM-to-SM speed differences.
+    // Two-level schedule: big chunks for the bulk, then quarter-size chunks for the last big chunk
+    // per warp, so the tail -- warps finishing at different times while the memory system drains --
+    // is a few microseconds instead of one big chunk's worth (the ticket counter is one address:
+    // smaller tail chunks or a longer tail region would make the atomics the bottleneck).
     const int kChunkRows = a.chunk_rows >= kRowsPerIter ? (a.chunk_rows / kRowsPerIter) * kRowsPerIter : kRowsPerIter;
-    const int64_t n_chunks = (n + kChunkRows - 1) / kChunkRows;
+    const int kSmallRows = kChunkRows / 4 >= kRowsPerIter ? (kChunkRows / 4 / kRowsPerIter) * kRowsPerIter : kRowsPerIter;
+    int64_t n_big = n / kChunkRows - total_warps;              // big chunks handed out before the tail
+    if (n_big < 0) n_big = 0;
+    const int64_t tail_row0 = n_big * kChunkRows;
+    const int64_t n_small = (n - tail_row0 + kSmallRows - 1) / kSmallRows;
+    const int64_t n_chunks = n_big + n_small;
     unsigned int *counter = a.work_counters + blockIdx.y;
     int64_t chunk = gwarp;
     unsigned int ticket = 0;                                  // lane 0: result of the in-flight atomic
@@ -94,7 +103,9 @@ gemv_scan_kernel(ScanArgs a) {
     for (; chunk < n_chunks;
          chunk = total_warps + int64_t(__shfl_sync(kFull, ticket, 0)),
          ticket = (lane == 0 && chunk < n_chunks) ? atomicAdd(counter, 1u) : 0u)
-    for (int64_t base = chunk * kChunkRows, cend = base + kChunkRows; base < cend && base < n; base += kRowsPerIter) {
+    for (int64_t base = chunk < n_big ? chunk * kChunkRows : tail_row0 + (chunk - n_big) * kSmallRows,
+                 cend = chunk < n_big ? base + kChunkRows : base + kSmallRows;
+         base < cend && base < n; base += kRowsPerIter) {
         uint4 ca[U][3], cb[U][3];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
