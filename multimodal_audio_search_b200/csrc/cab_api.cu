@@ -42,6 +42,8 @@ struct cab_index {
     double *d_w64 = nullptr;       // views into d_params, set by stage_params
     float *d_w32 = nullptr;
     int staged_nq = 0;             // number of queries whose weights are currently staged
+    bool inline_w_valid = false;   // the last search carried one query's weights inline
+    double inline_w64[2] = {0, 0};
     uint64_t *d_partial_keys = nullptr;  size_t sz_pkeys = 0;
     cab_candidate *d_cands = nullptr;    size_t sz_cands = 0;
     uint8_t *d_out = nullptr;      size_t d_out_bytes = 0;  // packed outputs
@@ -626,6 +628,7 @@ static int stage_params(cab_index *idx, const float *queries, int queries_loc, c
     idx->d_w64 = reinterpret_cast<double *>(idx->d_params);
     idx->d_w32 = reinterpret_cast<float *>(idx->d_params + size_t(nq) * 16);
     idx->staged_nq = nq;
+    idx->inline_w_valid = false;
     if (dq) *dq = qbytes ? reinterpret_cast<const float *>(idx->d_params + wbytes) : queries;
     return CAB_OK;
 }
@@ -662,12 +665,27 @@ static int run_local(cab_index *idx, const float *queries, int queries_loc, cons
     int rc = ensure_workspace(idx, nq, k, n_partials, use_gemm ? kGemmQueriesPerPass : batch,
                               use_gemm ? kGemmListCap : k, use_gemm ? gemm_workspace_bytes(nq, k, idx->sm_count) : 0);
     if (rc != CAB_OK) return rc;
+    // One query: parameters travel in the kernel arguments, no H2D copy ahead of the scan.
+    InlineParams inl{};
     const float *dq = nullptr;
-    if ((rc = stage_params(idx, queries, queries_loc, w_asr, w_audio, nq, s, &dq))) return rc;
+    if (nq == 1 && !use_gemm) {
+        const double tot = w_asr[0] + w_audio[0];
+        inl.use_weights = 1;
+        inl.wa32 = tot > 0 ? float(w_asr[0] / tot) : 0.f;
+        inl.wb32 = tot > 0 ? float(w_audio[0] / tot) : 0.f;
+        inl.w64_asr = w_asr[0]; inl.w64_audio = w_audio[0];
+        if (queries_loc == CAB_HOST) { inl.use_query = 1; memcpy(inl.q, queries, sizeof inl.q); dq = reinterpret_cast<const float *>(idx->d_params); }
+        else dq = queries;
+        idx->d_w64 = reinterpret_cast<double *>(idx->d_params);          // not read when inline_weights is set
+        idx->d_w32 = reinterpret_cast<float *>(idx->d_params + 16);
+        idx->staged_nq = 0;
+        idx->inline_w_valid = true; idx->inline_w64[0] = w_asr[0]; idx->inline_w64[1] = w_audio[0];
+    } else if ((rc = stage_params(idx, queries, queries_loc, w_asr, w_audio, nq, s, &dq))) return rc;
 
     EmitArgs ea{};
     if (out && (rc = make_emit(idx, 1, nq, k, threshold, out->index, out->fusion, out->asr, out->audio,
                                out->flags, out->count, out->loc, &ea))) return rc;
+    if (inl.use_weights) { ea.inline_weights = 1; ea.w64_asr = inl.w64_asr; ea.w64_audio = inl.w64_audio; }
     idx->timed = false;
     cab_candidate *cands = cand_dst ? cand_dst : idx->d_cands;      // sharded search: straight into the caller's block
     if (idx->size == 0) {
@@ -683,8 +701,10 @@ static int run_local(cab_index *idx, const float *queries, int queries_loc, cons
     sa.dtype = idx->dtype; sa.k = k;
     sa.select_threshold = float(threshold) - 1e-6f;
     sa.partial_keys = idx->d_partial_keys;
+    sa.inl = inl;
     sa.n_partials = n_partials; sa.nonfinite = idx->d_nonfinite; sa.work_counters = idx->d_counters; sa.chunk_rows = idx->opt_chunk_rows ? int(idx->opt_chunk_rows) : (idx->dtype == CAB_BF16 ? 64 : 32);
     FinalizeArgs fa{};
+    fa.inl = inl;
     fa.asr = idx->asr; fa.audio = idx->audio; fa.flags = idx->flags; fa.dtype = idx->dtype;
     fa.row_base = idx->row_base; fa.k = k; fa.partial_keys = idx->d_partial_keys;
     fa.n_partials = n_partials; fa.force_general = int(idx->opt_finalize_general);
@@ -800,7 +820,8 @@ int cab_merge_candidates(cab_index *idx, const cab_candidate *cands_device, int 
     CHECK_HANDLE(idx);
     if (!cands_device || n_lists <= 0 || (!w_asr) != (!w_audio)) return fail(idx, CAB_ERR_INVALID, "bad merge arguments");
     // w_asr == w_audio == NULL: reuse the weights staged by the preceding cab_search_candidates
-    if (!w_asr && idx->staged_nq != n_queries) return fail(idx, CAB_ERR_INVALID, "no staged weights for %d queries", n_queries);
+    const bool reuse_inline = !w_asr && n_queries == 1 && idx->inline_w_valid;
+    if (!w_asr && !reuse_inline && idx->staged_nq != n_queries) return fail(idx, CAB_ERR_INVALID, "no staged weights for %d queries", n_queries);
     if (n_queries <= 0 || n_queries > CAB_MAX_QUERIES || k <= 0 || k > CAB_MAX_K) return fail(idx, CAB_ERR_INVALID, "bad n_queries / k");
     if (size_t(n_lists) * k > 1024) return fail(idx, CAB_ERR_INVALID, "n_lists * k must be <= 1024");
     if (out_loc != CAB_HOST && out_loc != CAB_DEVICE) return fail(idx, CAB_ERR_INVALID, "out_loc");
@@ -814,6 +835,7 @@ int cab_merge_candidates(cab_index *idx, const cab_candidate *cands_device, int 
     if ((rc = make_emit(idx, n_lists, n_queries, k, threshold, out_index, out_fusion, out_asr,
                         out_audio, out_flags, out_count, out_loc, &ea))) return rc;
     ea.cands = cands_device;
+    if (reuse_inline) { ea.inline_weights = 1; ea.w64_asr = idx->inline_w64[0]; ea.w64_audio = idx->inline_w64[1]; }
     launch_emit(ea, s);
     idx->launches += 1;
     CU(idx, cudaGetLastError());
@@ -891,6 +913,7 @@ int cab_search_sharded(cab_index *idx, const float *queries, int queries_loc, co
     if ((rc = make_emit(idx, idx->peer_world, n_queries, k, threshold, out_index, out_fusion, out_asr,
                         out_audio, out_flags, out_count, out_loc, &ea))) return rc;
     ea.cands = pp.bufs[idx->peer_rank];
+    if (n_queries == 1 && idx->inline_w_valid) { ea.inline_weights = 1; ea.w64_asr = idx->inline_w64[0]; ea.w64_audio = idx->inline_w64[1]; }
     ea.wait_flags = pp.flags[idx->peer_rank] + pp.parity * idx->peer_world;
     ea.wait_epoch = epoch;
     ea.status = idx->d_status;

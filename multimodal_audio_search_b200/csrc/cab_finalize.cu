@@ -280,7 +280,8 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, E
 
     // ---- re-score the winners: one lane group per row, same operation order as the scan ---------
     float q[TR::NQ];
-    load_query<DT>(a.queries + size_t(qi) * kDim, lane, q);
+    const float *qsrc = a.queries + size_t(qi) * kDim;
+    load_query<DT>([&](int i) { return a.inl.use_query ? a.inl.q[i] : qsrc[i]; }, lane, q);
     const int g = lane & (TR::G - 1), sub = lane / TR::G;
     const uint4 *__restrict__ A = reinterpret_cast<const uint4 *>(a.asr);
     const uint4 *__restrict__ B = reinterpret_cast<const uint4 *>(a.audio);
@@ -321,7 +322,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, E
     // ---- fused emit (single candidate list): rank the <= k candidates by counting ----------------
     __syncthreads();
     uint64_t *score = s_sort;                                        // reuse the selection buffer
-    const double wa = e.w_asr[qi], wb = e.w_audio[qi];
+    const double wa = e.inline_weights ? e.w64_asr : e.w_asr[qi], wb = e.inline_weights ? e.w64_audio : e.w_audio[qi];
     const int t = threadIdx.x;
     if (t < a.k) score[t] = reference_fusion(s_cand[t], wa, wb, e.threshold);
     __syncthreads();
@@ -379,7 +380,7 @@ __global__ void __launch_bounds__(kEmitThreads) emit_kernel(EmitArgs a) {
     const int n_cand = a.n_lists * a.k;
     int np2 = 64;
     while (np2 < n_cand) np2 <<= 1;
-    const double wa = a.w_asr[qi], wb = a.w_audio[qi];
+    const double wa = a.inline_weights ? a.w64_asr : a.w_asr[qi], wb = a.inline_weights ? a.w64_audio : a.w_audio[qi];
     if (threadIdx.x == 0) s_n = 0;
     if (a.wait_flags) {
         // peer exchange: every rank's candidates of this epoch must have landed in our buffer

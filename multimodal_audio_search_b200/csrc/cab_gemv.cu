@@ -60,9 +60,10 @@ gemv_scan_kernel(ScanArgs a) {
     for (int t = 0; t < QT; ++t) {
         const bool valid = q0 + t < a.n_queries;
         const int qi = valid ? q0 + t : q0;       // pad the group with its first query, never pushed
-        bool ok = load_query<DT>(a.queries + size_t(qi) * kDim, lane, q[t]);
+        const float *qsrc = a.queries + size_t(qi) * kDim;
+        bool ok = load_query<DT>([&](int i) { return a.inl.use_query ? a.inl.q[i] : qsrc[i]; }, lane, q[t]);
         if (!ok && lane == 0) *a.nonfinite = 1;
-        w[t] = ScanWeights{a.wa32[qi], a.wb32[qi]};
+        w[t] = a.inl.use_weights ? ScanWeights{a.inl.wa32, a.inl.wb32} : ScanWeights{a.wa32[qi], a.wb32[qi]};
         top[t].init(s_keys[warp][t], a.k, valid ? bound_key(a.select_threshold) : ~0ull);
     }
 

@@ -27,6 +27,16 @@ void launch_synth_flags(uint32_t seed, int partial, int64_t r0, int64_t n, uint8
 void launch_widen_rows(const void *src, int dtype, int64_t r0, int64_t n, float *out,
                        cudaStream_t s);
 
+// Single-query searches carry their parameters in the kernel arguments (no H2D copy ahead of the
+// scan): the weights always, the raw query vector too when it comes from host memory.
+struct InlineParams {
+    int use_weights;           // wa32/wb32/w64 below are valid (n_queries == 1)
+    int use_query;             // q below is valid
+    float wa32, wb32;
+    double w64_asr, w64_audio;
+    float q[CAB_DIM];
+};
+
 // ---- scan (cab_gemv.cu) ------------------------------------------------------------------------
 struct ScanArgs {
     const void *asr;           // [n_rows x 384] normalised rows, fp32 or bf16
@@ -48,6 +58,7 @@ struct ScanArgs {
     int *nonfinite;            // set if a query holds NaN/Inf
     unsigned int *work_counters;   // GEMV: [n_queries] chunk tickets, zero on entry (finalize resets them)
     int chunk_rows;                // GEMV: rows per dynamically scheduled chunk
+    InlineParams inl;
 };
 struct GemvConfig {
     int variant;               // 0 = LDG register pipeline (the only one built)
@@ -104,6 +115,7 @@ struct FinalizeArgs {
     int force_general;         // test hook: skip the head-bound fast path
     unsigned int *work_counters;   // [n_queries] reset to 0 for the next scan (may be null)
     PeerPush peer;
+    InlineParams inl;
 };
 struct EmitArgs;
 // fused_emit != nullptr (single candidate list): the emit stage runs inside the same kernel.
@@ -116,6 +128,8 @@ struct EmitArgs {
     int k;
     const double *w_asr;          // device [n_queries]
     const double *w_audio;
+    int inline_weights;           // n_queries == 1: use w64_asr / w64_audio instead of the arrays
+    double w64_asr, w64_audio;
     double threshold;
     int64_t *out_index;           // device [n_queries][k] (all required here)
     double *out_fusion;

@@ -31,15 +31,15 @@ template <> struct RowTraits<CAB_BF16> {
 // Normalised query elements this lane multiplies with (sklearn normalize(X): x / sqrt(sum x^2),
 // zero norm -> 1).  Every warp computes the norm with the same order, so all agree bit-for-bit.
 // Returns false (warp-uniform) if the query holds NaN/Inf.
-template <int DT>
-__device__ __forceinline__ bool load_query(const float *__restrict__ q_raw, int lane,
-                                           float (&q)[RowTraits<DT>::NQ]) {
+// `get(i)` returns raw query element i (global memory, or the kernel-argument copy).
+template <int DT, typename Get>
+__device__ __forceinline__ bool load_query(Get get, int lane, float (&q)[RowTraits<DT>::NQ]) {
     using TR = RowTraits<DT>;
     float ss = 0.f;
     bool bad = false;
 #pragma unroll
     for (int i = 0; i < kDim / 32; ++i) {
-        float x = q_raw[lane + 32 * i];
+        float x = get(lane + 32 * i);
         bad |= !isfinite(x);
         ss = fmaf(x, x, ss);
     }
@@ -52,7 +52,7 @@ __device__ __forceinline__ bool load_query(const float *__restrict__ q_raw, int 
 #pragma unroll
     for (int j = 0; j < 3; ++j)
 #pragma unroll
-        for (int e = 0; e < TR::EPC; ++e) q[j * TR::EPC + e] = q_raw[(g + TR::G * j) * TR::EPC + e] / norm;
+        for (int e = 0; e < TR::EPC; ++e) q[j * TR::EPC + e] = get((g + TR::G * j) * TR::EPC + e) / norm;
     return !bad;
 }
 
