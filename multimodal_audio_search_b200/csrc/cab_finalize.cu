@@ -131,12 +131,14 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, E
     __shared__ uint64_t s_sort[kSortCap];
     __shared__ cab_candidate s_cand[kMaxK];
     __shared__ uint64_t s_head[kMaxHeads];
+    __shared__ float s_q[kDim];
     __shared__ int s_cnt;
     __shared__ uint64_t s_bound;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int qi = blockIdx.x;
     if (threadIdx.x == 0) { s_cnt = 0; s_bound = 0ull; if (a.work_counters) a.work_counters[qi] = 0u; }
+    if (a.inl.use_query && threadIdx.x < kDim) s_q[threadIdx.x] = a.inl.q[threadIdx.x];   // kernel-argument query
     __syncthreads();
 
     // Sort the buffer, keep the best k, raise the bound.  Block-uniform.
@@ -281,7 +283,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, E
     // ---- re-score the winners: one lane group per row, same operation order as the scan ---------
     float q[TR::NQ];
     const float *qsrc = a.queries + size_t(qi) * kDim;
-    load_query<DT>([&](int i) { return a.inl.use_query ? a.inl.q[i] : qsrc[i]; }, lane, q);
+    load_query<DT>([&](int i) { return a.inl.use_query ? s_q[i] : qsrc[i]; }, lane, q);
     const int g = lane & (TR::G - 1), sub = lane / TR::G;
     const uint4 *__restrict__ A = reinterpret_cast<const uint4 *>(a.asr);
     const uint4 *__restrict__ B = reinterpret_cast<const uint4 *>(a.audio);

@@ -48,6 +48,13 @@ gemv_scan_kernel(ScanArgs a) {
     extern __shared__ __align__(16) uint8_t scan_smem[];
     uint64_t(*s_keys)[QT][kWarpCap] = reinterpret_cast<uint64_t(*)[QT][kWarpCap]>(scan_smem);
     int(*s_count)[QT] = reinterpret_cast<int(*)[QT]>(scan_smem + sizeof(uint64_t) * kScanWarps * QT * kWarpCap);
+    float *s_q = reinterpret_cast<float *>(scan_smem + sizeof(uint64_t) * kScanWarps * QT * kWarpCap + sizeof(int) * kScanWarps * QT);
+    if (a.inl.use_query) {
+        // Kernel-argument query -> shared memory once per CTA (per-lane indexed reads of the
+        // constant bank serialise 32-way; done by every warp they cost ~10 us per scan).
+        for (int i = threadIdx.x; i < kDim; i += kScanThreads) s_q[i] = a.inl.q[i];
+        __syncthreads();
+    }
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q0 = blockIdx.y * QT;               // first query of this CTA's group
@@ -61,7 +68,7 @@ gemv_scan_kernel(ScanArgs a) {
         const bool valid = q0 + t < a.n_queries;
         const int qi = valid ? q0 + t : q0;       // pad the group with its first query, never pushed
         const float *qsrc = a.queries + size_t(qi) * kDim;
-        bool ok = load_query<DT>([&](int i) { return a.inl.use_query ? a.inl.q[i] : qsrc[i]; }, lane, q[t]);
+        bool ok = load_query<DT>([&](int i) { return a.inl.use_query ? s_q[i] : qsrc[i]; }, lane, q[t]);
         if (!ok && lane == 0) *a.nonfinite = 1;
         w[t] = a.inl.use_weights ? ScanWeights{a.inl.wa32, a.inl.wb32} : ScanWeights{a.wa32[qi], a.wb32[qi]};
         top[t].init(s_keys[warp][t], a.k, valid ? bound_key(a.select_threshold) : ~0ull);
@@ -216,7 +223,7 @@ int gemv_max_grid(int sm_count) { return sm_count * 4; }
 
 template <int DT, int U, int MB, int QT>
 static void launch_one(const ScanArgs &a, dim3 grid, cudaStream_t s) {
-    constexpr size_t smem = sizeof(uint64_t) * kScanWarps * QT * kWarpCap + sizeof(int) * kScanWarps * QT;
+    constexpr size_t smem = sizeof(uint64_t) * kScanWarps * QT * kWarpCap + sizeof(int) * kScanWarps * QT + sizeof(float) * kDim;
     static bool attr_done = false;
     if (smem > 48 * 1024 && !attr_done) {
         cudaFuncSetAttribute(gemv_scan_kernel<DT, U, MB, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));

@@ -9,7 +9,7 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
 seed, n = 99, 300_001
-for dtype, nq, k, path in (("fp32", 3, 10, "gemv"), ("bf16", 70, 100, "gemm"), ("fp32", 40, 37, "gemv")):
+for dtype, nq, k, path in (("fp32", 1, 10, "gemv"), ("fp32", 3, 10, "gemv"), ("bf16", 70, 100, "gemm"), ("fp32", 40, 37, "gemv"), ("bf16", 1, 100, "gemv")):
     lo, hi = shard_range(n, rank, world)
     idx = SegmentIndex(dtype, capacity=hi - lo, device=local)
     idx.append_synth(seed, n, lo, hi, n_queries=nq, plants=40, partial=True)
