@@ -259,7 +259,8 @@ int cab_index_append(cab_index *idx, const float *asr_rows, const float *audio_r
     CU(idx, cudaSetDevice(idx->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : idx->own_stream;
     if (idx->size + n_rows > idx->capacity) {
-        int rc = grow(idx, std::max(idx->size + n_rows, idx->capacity * 2));
+        int rc = grow(idx, std::max(idx->size + n_rows, idx->capacity * 2));        // geometric growth
+        if (rc == CAB_ERR_NOMEM && idx->capacity * 2 > idx->size + n_rows) rc = grow(idx, idx->size + n_rows);   // ... or exact fit
         if (rc != CAB_OK) return rc;
     }
     const int64_t dst0 = idx->size;
@@ -341,7 +342,8 @@ int cab_index_append_synth(cab_index *idx, uint32_t seed, int64_t n_total, int64
     CU(idx, cudaSetDevice(idx->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : idx->own_stream;
     if (idx->size + n_rows > idx->capacity) {
-        int rc = grow(idx, std::max(idx->size + n_rows, idx->capacity * 2));
+        int rc = grow(idx, std::max(idx->size + n_rows, idx->capacity * 2));        // geometric growth
+        if (rc == CAB_ERR_NOMEM && idx->capacity * 2 > idx->size + n_rows) rc = grow(idx, idx->size + n_rows);   // ... or exact fit
         if (rc != CAB_OK) return rc;
     }
     const SynthParams p = make_synth(seed, n_total, n_queries, plants);
