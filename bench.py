@@ -352,7 +352,7 @@ def main():
             "gpu_launches": int(launches), "roofline": roof, "clocks": clocks,
             "build_s": t_build,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # the CPU baseline is reported at N=1 only
             out["cpu_baseline"] = cpu_baseline(n_rows, dtype, k)
         print(json.dumps(out))
     if world > 1:
