@@ -137,6 +137,9 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, E
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int qi = blockIdx.x;
+    // Launched with programmatic stream serialization: the CTA is already resident when the scan
+    // finishes; everything the scan wrote is visible after this wait.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (threadIdx.x == 0) { s_cnt = 0; s_bound = 0ull; if (a.work_counters) a.work_counters[qi] = 0u; }
     if (a.inl.use_query && threadIdx.x < kDim) s_q[threadIdx.x] = a.inl.q[threadIdx.x];   // kernel-argument query
     __syncthreads();
@@ -364,8 +367,16 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, E
 void launch_finalize(const FinalizeArgs &a, const EmitArgs *fused_emit, cudaStream_t s) {
     EmitArgs e{};
     if (fused_emit) e = *fused_emit;
-    if (a.dtype == CAB_BF16) finalize_kernel<CAB_BF16><<<a.n_queries, kFinThreads, 0, s>>>(a, e);
-    else finalize_kernel<CAB_F32><<<a.n_queries, kFinThreads, 0, s>>>(a, e);
+    // Programmatic dependent launch: the finalize grid is staged while the scan still runs and
+    // starts the moment it completes (the kernel begins with griddepcontrol.wait).
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(a.n_queries); cfg.blockDim = dim3(kFinThreads); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (a.dtype == CAB_BF16) cudaLaunchKernelEx(&cfg, finalize_kernel<CAB_BF16>, a, e);
+    else cudaLaunchKernelEx(&cfg, finalize_kernel<CAB_F32>, a, e);
 }
 
 // ---- emit (merge of several candidate lists: sharded search) ---------------------------------------

@@ -63,13 +63,14 @@ gemv_scan_kernel(ScanArgs a) {
     float q[QT][TR::NQ];
     ScanWeights w[QT];
     WarpTopK top[QT];
+    bool all_finite = true;
 #pragma unroll
     for (int t = 0; t < QT; ++t) {
         const bool valid = q0 + t < a.n_queries;
         const int qi = valid ? q0 + t : q0;       // pad the group with its first query, never pushed
         const float *qsrc = a.queries + size_t(qi) * kDim;
         bool ok = load_query<DT>([&](int i) { return a.inl.use_query ? s_q[i] : qsrc[i]; }, lane, q[t]);
-        if (!ok && lane == 0) *a.nonfinite = 1;
+        all_finite &= ok;
         w[t] = a.inl.use_weights ? ScanWeights{a.inl.wa32, a.inl.wb32} : ScanWeights{a.wa32[qi], a.wb32[qi]};
         top[t].init(s_keys[warp][t], a.k, valid ? bound_key(a.select_threshold) : ~0ull);
     }
@@ -105,6 +106,11 @@ gemv_scan_kernel(ScanArgs a) {
     const int64_t n_chunks = n_big + n_small;
     unsigned int *counter = a.work_counters + blockIdx.y;
     int64_t chunk = gwarp;
+    // Programmatic dependent launch: everything above (query staging + normalisation) may overlap
+    // the previous search's finalize kernel; the ticket counter (reset by that kernel) and the
+    // partial-key slots (read by it) are only touched after this wait.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (!all_finite && lane == 0) *a.nonfinite = 1;           // NaN/Inf query: sklearn raises ValueError
     unsigned int ticket = 0;                                  // lane 0: result of the in-flight atomic
     if (chunk < n_chunks && lane == 0) ticket = atomicAdd(counter, 1u);
 
@@ -229,7 +235,13 @@ static void launch_one(const ScanArgs &a, dim3 grid, cudaStream_t s) {
         cudaFuncSetAttribute(gemv_scan_kernel<DT, U, MB, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         attr_done = true;
     }
-    gemv_scan_kernel<DT, U, MB, QT><<<grid, kScanThreads, smem, s>>>(a);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = dim3(kScanThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, gemv_scan_kernel<DT, U, MB, QT>, a);
 }
 
 template <int DT>
