@@ -183,7 +183,7 @@ CAB_API int cab_search_sharded(cab_index *idx, const float *queries, int queries
 /* ---- tuning / introspection -------------------------------------------------------------- */
 /* Options: "gemv_unroll" (row-steps in flight per warp: 1/2/4/8, 0 = default),
  * "gemv_blocks_per_sm" (resident CTAs per SM, 0 = default), "gemv_query_tile" (queries scored per
- * corpus pass, 1/2/4, 0 = default: fp32 4, bf16 2), "gemv_batch", "gemm_min_queries",
+ * corpus pass, 1/2/4, 0 = default 4), "gemv_batch", "gemm_min_queries",
  * "time_kernels", "sync_after_search"; unknown keys fail. */
 CAB_API int cab_index_set_option(cab_index *idx, const char *key, int64_t value);
 CAB_API int64_t cab_index_get_option(const cab_index *idx, const char *key);

@@ -42,15 +42,16 @@ for dtype in dtypes:
     idx = SegmentIndex(dtype, capacity=rows)
     idx.append_synth(1, rows, 0, rows, n_queries=8, plants=30)
     idx.set_option("time_kernels", 1)
-    for tile in (1, 2, 4):
-        if dtype == "bf16" and tile == 4:
+    for tile, unroll in ((1, 0), (2, 0), (4, 0), (4, 4)):
+        if dtype == "bf16" and unroll == 4:
             continue
         idx.set_option("gemv_query_tile", tile)
+        idx.set_option("gemv_unroll", unroll)
         ms = []
         for i in range(8):
             idx.search(q[:32], 0.5, 0.5, k=10, path="gemv")
             ms.append(idx.last_scan_ms())
         ms = float(np.mean(ms[2:]))
-        print(json.dumps({"rows": rows, "dtype": dtype, "query_tile": tile, "batch": 32, "scan_ms_total": ms,
+        print(json.dumps({"rows": rows, "dtype": dtype, "query_tile": tile, "unroll": unroll, "batch": 32, "scan_ms_total": ms,
                           "queries_per_s": 32e3 / ms, "corpus_passes": 32 // tile}), flush=True)
     idx.close()
