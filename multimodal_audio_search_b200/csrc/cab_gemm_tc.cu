@@ -26,6 +26,10 @@
 //     compares with its private running bound (one compare rejects almost every segment) and
 //     appends survivors to its private candidate list in global memory (L2 resident); a full
 //     list is compacted warp-cooperatively (bitonic sort in shared memory, keep k).
+//   * cross-CTA bound sharing: every appended candidate bumps a per-query score-level histogram in
+//     global memory (one RED); each epilogue warp refreshes one query's bound per tile from the
+//     histogram's suffix sums (>= k candidates at or above a level => the global k-th best is at
+//     least that level).  Without it pruning stays at the 0.1 threshold for the whole scan.
 //   Roofline: 2 x 2 x 384 flop per (query, segment); at 256 queries the kernel needs 256 flop per
 //   corpus byte, i.e. it sits on the HBM/tensor ridge.
 #include <cuda.h>
@@ -58,7 +62,7 @@ constexpr float kLevelStep = 0.004f;
 // smem layout (dynamic, 1024-byte aligned)
 constexpr uint32_t kOffQ = 0;
 constexpr uint32_t kOffRing = kOffQ + kNumKBlocks * kQBlockBytes;                  // 98304
-constexpr uint32_t kOffScratch = kOffRing + kStages * kStageBytes;                 // 196608
+constexpr uint32_t kOffScratch = kOffRing + kStages * kStageBytes;                 // 98304 + 114688 = 212992
 constexpr uint32_t kOffBars = kOffScratch + 4 * kWarpCap * 8;                      // + 8 KB sort scratch
 constexpr uint32_t kNumBars = 2 * kStages + 4 + 1;
 constexpr uint32_t kOffTmemPtr = kOffBars + kNumBars * 8;

@@ -308,3 +308,31 @@ def test_config2_one_million_fp32():
     bi, bf, _, _, _ = result_row(rb)
     assert len(set(bi) & set(oi)) >= 10
     np.testing.assert_allclose(np.sort(bf)[::-1], of, atol=BF16_TOL, rtol=0)
+
+
+def test_invalid_arguments_are_rejected_not_computed():
+    import ctypes as C
+    from multimodal_audio_search_b200 import _native as N
+    idx = SegmentIndex("fp32")
+    a, b, f, _ = synth.library(2, 40, 1, 5)
+    idx.append(a, b, f)
+    q = synth.raw_queries(2, 0, 1)
+    for kwargs in ({"k": 0}, {"k": 129}, {"threshold": float("nan")}, {"path": "gemm"}):
+        with pytest.raises((N.CabError, KeyError)):
+            idx.search(q, 0.5, 0.5, **kwargs)
+    with pytest.raises(N.CabError):
+        idx.search(q, -0.1, 0.5)                         # weights must be >= 0
+    with pytest.raises(ValueError):
+        idx.search(np.zeros((1, 100), np.float32))       # wrong dimension
+    with pytest.raises(ValueError):
+        idx.append(a[:, :100], b, f)
+    big = np.zeros((4097, 384), np.float32)
+    with pytest.raises(N.CabError):
+        idx.search(big)                                  # > CAB_MAX_QUERIES per call
+    lib = N.lib()
+    assert lib.cab_search(idx._h, None, 0, None, None, 1, 10, 0.1, 0, None, None, None, None, None, None, 0, None) == N.CAB_ERR_INVALID
+    assert b"null" in lib.cab_last_error(idx._h)
+    res = idx.search(q)                                  # the handle is still healthy
+    assert res.count[0] >= 1
+    with pytest.raises(N.CabError):
+        SegmentIndex("fp32", device=99)
