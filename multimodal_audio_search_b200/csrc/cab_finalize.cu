@@ -393,6 +393,7 @@ __global__ void __launch_bounds__(kEmitThreads) emit_kernel(EmitArgs a) {
     const int n_cand = a.n_lists * a.k;
     int np2 = 64;
     while (np2 < n_cand) np2 <<= 1;
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // programmatic dependent launch (see launch_emit)
     const double wa = a.inline_weights ? a.w64_asr : a.w_asr[qi], wb = a.inline_weights ? a.w64_audio : a.w_audio[qi];
     if (threadIdx.x == 0) s_n = 0;
     if (a.wait_flags) {
@@ -488,7 +489,13 @@ __global__ void __launch_bounds__(kEmitThreads) emit_kernel(EmitArgs a) {
 }
 
 void launch_emit(const EmitArgs &a, cudaStream_t s) {
-    emit_kernel<<<a.n_queries, kEmitThreads, 0, s>>>(a);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(a.n_queries); cfg.blockDim = dim3(kEmitThreads); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, emit_kernel, a);
 }
 
 }  // namespace cab
