@@ -65,6 +65,11 @@ typedef enum cab_path {                                              /* which sc
  * as an all-zero row: its cosine is exactly 0.0 like the reference's. */
 #define CAB_FLAG_ASR 1u
 #define CAB_FLAG_AUDIO 2u
+/* Bits 2-3 of the flag byte: the row's weight class (0..3), read only by cab_score_all (the
+ * earlier engine's per-row weighting, previous_iterations/streamlit_app.py:214-219); the top-k
+ * search ignores them and hands them back untouched in out_flags. */
+#define CAB_FLAG_CLASS_SHIFT 2
+#define CAB_FLAG_CLASS_MASK 0x0Cu
 
 CAB_API int cab_version(void);
 CAB_API const char *cab_status_string(int status);
@@ -160,6 +165,21 @@ CAB_API int cab_merge_candidates(cab_index *idx, const cab_candidate *cands_devi
                          double threshold, int64_t *out_index, double *out_fusion, float *out_asr,
                          float *out_audio, uint8_t *out_flags, int32_t *out_count, int out_loc,
                          void *stream);
+
+/* ---- legacy scoring modes: every segment's fused similarity, no threshold, no top-k ------------
+ * Replaces the per-item loop of the reference's earlier engine, `UnifiedAudioSearch.search`
+ * (previous_iterations/streamlit_app.py:173-223), which returns np.array(similarities) over the
+ * whole database for strategy "asr_only" / "caption_only" / "adaptive".
+ *   out[q][r] = class_weights[q][c][0] * cos(query q, asr row r)
+ *             + class_weights[q][c][1] * cos(query q, audio row r),    c = weight class of row r
+ * in fp32 with the products and the sum rounded separately (numpy float32 scalar arithmetic); a
+ * missing embedding (zero row) contributes 0.0; no success gating, no renormalisation.
+ * class_weights: HOST float [n_queries][4][2].  asr_only = {1,0} for every class, caption_only =
+ * {0,1}, adaptive = class 0 {0.2,0.8}, class 1 {0.7,0.3} with class 1 = "transcript longer than
+ * 10 characters" (:216).  out: [n_queries][cab_index_size] floats, host or device.
+ * A NaN/Inf query: CAB_ERR_NONFINITE with host output; all-NaN scores with device output. */
+CAB_API int cab_score_all(cab_index *idx, const float *queries, int queries_loc, int n_queries,
+                  const float *class_weights, float *out, int out_loc, void *stream);
 
 /* ---- sharded search with the exchange fused into the kernels (NVLink peer memory) ---------------
  * Instead of steps 2+3 above through NCCL: the finalize kernel of every rank stores its k

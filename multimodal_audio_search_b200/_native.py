@@ -69,6 +69,7 @@ SIGNATURES = {
     "cab_index_get_option": (_i64, [_p, C.c_char_p]),
     "cab_index_launch_count": (_i64, [_p]),
     "cab_index_last_scan_ms": (_dbl, [_p]),
+    "cab_score_all": (_i32, [_p, _p, _i32, _i32, _p, _p, _i32, _p]),
 }
 
 _lib = None

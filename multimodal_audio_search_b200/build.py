@@ -22,7 +22,7 @@ TORCH_LIB = os.path.join(HERE, "libcab_torch.so")
 TORCH_SRC = os.path.join(CSRC, "torch_binding.cpp")
 
 SOURCES = ["cab_api.cu", "cab_ingest.cu", "cab_gemv.cu", "cab_finalize.cu",
-           "cab_gemm_tc.cu"]
+           "cab_gemm_tc.cu", "cab_score_all.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xptxas", "-v",
               "--expt-relaxed-constexpr"]

@@ -55,6 +55,7 @@ struct cab_index {
     uint8_t *h_out = nullptr; size_t h_out_bytes = 0;
     uint8_t *h_rows = nullptr; size_t h_rows_bytes = 0;
     float *d_rows = nullptr;  size_t d_rows_bytes = 0;   // raw-row device staging (append)
+    uint8_t *d_scores = nullptr; size_t d_scores_bytes = 0;   // cab_score_all with host output
     cudaEvent_t ev_in = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     bool ev_in_pending = false, timed = false;
     // options
@@ -199,7 +200,7 @@ int cab_index_destroy(cab_index *idx) {
     cudaFree(idx->asr); cudaFree(idx->audio); cudaFree(idx->flags);
     cudaFree(idx->d_params);
     cudaFree(idx->d_partial_keys); cudaFree(idx->d_cands);
-    cudaFree(idx->d_out); cudaFree(idx->d_gemm_ws); cudaFree(idx->d_nonfinite); cudaFree(idx->d_rows); cudaFree(idx->d_counters);
+    cudaFree(idx->d_out); cudaFree(idx->d_gemm_ws); cudaFree(idx->d_nonfinite); cudaFree(idx->d_rows); cudaFree(idx->d_counters); cudaFree(idx->d_scores);
     for (int r = 0; r < idx->peer_world; ++r)
         if (idx->peer_attached && r != idx->peer_rank && idx->peer_ptr[r]) cudaIpcCloseMemHandle(idx->peer_ptr[r]);
     cudaFree(idx->d_peer); cudaFree(idx->d_done); cudaFree(idx->d_status); cudaFree(idx->d_host_done);
@@ -842,6 +843,55 @@ int cab_merge_candidates(cab_index *idx, const cab_candidate *cands_device, int 
     idx->launches += 1;
     CU(idx, cudaGetLastError());
     return finish_outputs(idx, n_queries, k, o, s);
+}
+
+// ---- legacy modes: every segment's fused score ---------------------------------------------------
+int cab_score_all(cab_index *idx, const float *queries, int queries_loc, int n_queries,
+                  const float *class_weights, float *out, int out_loc, void *stream) {
+    CHECK_HANDLE(idx);
+    if (!queries || !class_weights || !out) return fail(idx, CAB_ERR_INVALID, "queries / class_weights / out are null");
+    if (queries_loc != CAB_HOST && queries_loc != CAB_DEVICE) return fail(idx, CAB_ERR_INVALID, "queries_loc");
+    if (out_loc != CAB_HOST && out_loc != CAB_DEVICE) return fail(idx, CAB_ERR_INVALID, "out_loc");
+    if (n_queries <= 0 || n_queries > CAB_MAX_QUERIES) return fail(idx, CAB_ERR_INVALID, "n_queries must be in 1..%d", CAB_MAX_QUERIES);
+    for (int i = 0; i < n_queries * 8; ++i)
+        if (!std::isfinite(class_weights[i])) return fail(idx, CAB_ERR_INVALID, "class weights must be finite");
+    if (idx->size == 0) return CAB_OK;
+    cudaStream_t s = stream ? (cudaStream_t)stream : idx->own_stream;
+    CU(idx, cudaSetDevice(idx->device));
+    const bool host_out = out_loc == CAB_HOST;
+    const size_t per_query = size_t(idx->size) * sizeof(float);
+    float *d_out = out;
+    if (host_out) {
+        int rc = ensure_dev(idx, &idx->d_scores, &idx->d_scores_bytes, per_query * n_queries);
+        if (rc != CAB_OK) return rc;
+        d_out = reinterpret_cast<float *>(idx->d_scores);
+    }
+    ScoreAllArgs a{};
+    a.asr = idx->asr; a.audio = idx->audio; a.flags = idx->flags; a.n_rows = idx->size; a.dtype = idx->dtype;
+    a.nonfinite = host_out ? idx->d_nonfinite : nullptr;     // device results: a bad query gives NaN scores
+    for (int q = 0; q < n_queries; ++q) {
+        if (queries_loc == CAB_HOST) { a.use_inline_query = 1; memcpy(a.q, queries + size_t(q) * CAB_DIM, sizeof a.q); }
+        else { a.use_inline_query = 0; a.query = queries + size_t(q) * CAB_DIM; }
+        memcpy(a.class_w, class_weights + size_t(q) * 8, sizeof a.class_w);
+        a.out = d_out + size_t(q) * idx->size;
+        launch_score_all(a, idx->sm_count, s);
+        idx->launches += 1;
+    }
+    CU(idx, cudaGetLastError());
+    if (!host_out) {
+        if (idx->opt_sync) CU(idx, cudaStreamSynchronize(s));
+        return CAB_OK;
+    }
+    int bad = 0;
+    CU(idx, cudaMemcpyAsync(out, d_out, per_query * n_queries, cudaMemcpyDeviceToHost, s));
+    CU(idx, cudaMemcpyAsync(&bad, idx->d_nonfinite, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(idx, cudaStreamSynchronize(s));
+    if (bad) {
+        CU(idx, cudaMemsetAsync(idx->d_nonfinite, 0, sizeof(int), s));
+        CU(idx, cudaStreamSynchronize(s));
+        return fail(idx, CAB_ERR_NONFINITE, "Input contains NaN or infinity (query)");
+    }
+    return CAB_OK;
 }
 
 // ---- peer-memory exchange ----------------------------------------------------------------------

@@ -341,7 +341,7 @@ gemm_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             const uint32_t row0 = uint32_t(tile * kTileRows);
             const uint32_t fw = flag_word;
             flag_word = load_flags(tile + p.n_pairs);                          // prefetch the next tile's flags
-            const bool fast = thr_nonneg && __all_sync(kFull, fw == 0x03030303u);
+            const bool fast = thr_nonneg && __all_sync(kFull, (fw & 0x03030303u) == 0x03030303u);   // bits 2-3: weight class, not used here
             {   // refresh the bound of lane (it & 31)'s query from the shared level histogram
                 int s_hi = lv_hi, s_lo = lv_lo;                                // inclusive suffix sums over lanes
 #pragma unroll

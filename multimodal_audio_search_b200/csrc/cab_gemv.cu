@@ -21,14 +21,6 @@ namespace cab {
 constexpr int kScanThreads = 256;
 constexpr int kScanWarps = kScanThreads / 32;
 
-// Empty asm that consumes and re-defines three loaded chunks: volatile asms keep their order, so
-// every use of the chunks is pinned after ALL the loads issued before this point.
-__device__ __forceinline__ void keep_live(uint4 (&c)[3]) {
-    asm volatile("" : "+r"(c[0].x), "+r"(c[0].y), "+r"(c[0].z), "+r"(c[0].w),
-                      "+r"(c[1].x), "+r"(c[1].y), "+r"(c[1].z), "+r"(c[1].w),
-                      "+r"(c[2].x), "+r"(c[2].y), "+r"(c[2].z), "+r"(c[2].w));
-}
-
 // MB (min resident CTAs per SM) is part of the contract with ptxas: without it ptxas caps the
 // kernel at 80 registers and interleaves loads with FMAs (7 loads in flight instead of 24).
 // QT = queries scored per corpus pass (register tiling): the rows are loaded once and multiplied

@@ -76,6 +76,22 @@ GemvPlan plan_gemv(const GemvConfig &cfg, int dtype, int n_queries, int sm_count
 int gemv_max_grid(int sm_count);       // upper bound of grid_x over all plans (buffer sizing)
 void launch_gemv_scan(const ScanArgs &a, const GemvPlan &plan, cudaStream_t s);
 
+// ---- legacy modes: all N fused scores, per-row weight class (cab_score_all.cu) --------------------
+struct ScoreAllArgs {
+    const void *asr;
+    const void *audio;
+    const uint8_t *flags;      // bits 2-3 of a row's byte: its weight class
+    int64_t n_rows;
+    int dtype;
+    const float *query;        // device, raw fp32 [384] (unused when use_inline_query)
+    int use_inline_query;
+    float q[CAB_DIM];          // host query, carried in the kernel arguments
+    float class_w[4][2];       // {w_asr, w_audio} per weight class
+    float *out;                // device [n_rows]; all NaN if the query holds NaN/Inf
+    int *nonfinite;            // also set in that case (may be null)
+};
+void launch_score_all(const ScoreAllArgs &a, int sm_count, cudaStream_t s);
+
 // ---- tensor-core scan (cab_gemm_tc.cu) -----------------------------------------------------------
 constexpr int kGemmListCap = 256;       // slots per (CTA pair, query) candidate list
 constexpr int kGemmQueriesPerPass = 256;

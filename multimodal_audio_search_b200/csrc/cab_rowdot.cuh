@@ -56,6 +56,14 @@ __device__ __forceinline__ bool load_query(Get get, int lane, float (&q)[RowTrai
     return !bad;
 }
 
+// Empty asm that consumes and re-defines three loaded chunks: volatile asms keep their order, so
+// every use of the chunks is pinned after ALL the loads issued before this point.
+__device__ __forceinline__ void keep_live(uint4 (&c)[3]) {
+    asm volatile("" : "+r"(c[0].x), "+r"(c[0].y), "+r"(c[0].z), "+r"(c[0].w),
+                      "+r"(c[1].x), "+r"(c[1].y), "+r"(c[1].z), "+r"(c[1].w),
+                      "+r"(c[2].x), "+r"(c[2].y), "+r"(c[2].z), "+r"(c[2].w));
+}
+
 // acc += <chunk j of a row, the lane's query elements for chunk j>
 template <int DT>
 __device__ __forceinline__ float dot_chunk(uint4 c, const float (&q)[RowTraits<DT>::NQ], int j, float acc) {

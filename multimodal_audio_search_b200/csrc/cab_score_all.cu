@@ -1,0 +1,113 @@
+// Legacy scoring modes: ONE fused similarity per segment, all N of them, no threshold, no top-k.
+//
+// Replaces the per-item loop of the reference's earlier engine
+// (previous_iterations/streamlit_app.py:173-223, `UnifiedAudioSearch.search`), which returns
+// np.array(similarities) over the whole database:
+//   asr_only     sim = cos(q, asr)                        (:188-193)
+//   caption_only sim = cos(q, caption)                    (:195-200)
+//   adaptive     sim = 0.7 cos_asr + 0.3 cos_cap   if len(transcript.strip()) > 10
+//                      0.2 cos_asr + 0.8 cos_cap   otherwise                      (:202-219)
+// A missing embedding contributes 0.0 (zero row in the index).  The per-row choice between weight
+// pairs is a 2-bit weight class kept in bits 2-3 of the row's flag byte; the caller passes a
+// 4-entry table {w_asr, w_audio} per class, so all three strategies (and any other per-row
+// weighting) are one kernel.  No success gating and no renormalisation here: that is the current
+// engine's rule (audio_search.py:654-670), served by the top-k scan.
+//
+// HBM-bound like the top-k scan: 2 x 384 x sizeof(elem) bytes read + 4 bytes written per segment.
+// Same load shape (U row-steps x 2 corpora x 3 LDG.128 per lane in flight, L1-bypassing), static
+// warp-cyclic row assignment (no selection, so no load imbalance to schedule around), plain
+// butterfly reduction (the issue slots are there: ~60 of ~500 per row are used).
+#include "cab_internal.h"
+#include "cab_rowdot.cuh"
+
+namespace cab {
+
+constexpr int kScoreThreads = 256;
+constexpr int kScoreWarps = kScoreThreads / 32;
+
+// MB = resident CTAs per SM, part of the register contract with ptxas exactly as in the top-k
+// scan: fp32 U=4 needs 96 registers for the loads in flight alone.
+template <int DT, int U, int MB>
+__global__ void __launch_bounds__(kScoreThreads, MB)
+score_all_kernel(ScoreAllArgs a) {
+    using TR = RowTraits<DT>;
+    constexpr int G = TR::G, RW = TR::RW, CPR = TR::CPR;
+    constexpr int kRowsPerIter = U * RW;
+
+    __shared__ float s_q[kDim];
+    if (a.use_inline_query) {
+        for (int i = threadIdx.x; i < kDim; i += kScoreThreads) s_q[i] = a.q[i];
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane & (G - 1), sub = lane / G;
+
+    float q[TR::NQ];
+    const float *qsrc = a.query;
+    const bool finite = load_query<DT>([&](int i) { return a.use_inline_query ? s_q[i] : qsrc[i]; }, lane, q);
+    if (!finite && a.nonfinite && blockIdx.x == 0 && threadIdx.x == 0) *a.nonfinite = 1;
+    float cw[4][2];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { cw[c][0] = a.class_w[c][0]; cw[c][1] = a.class_w[c][1]; }
+
+    const uint4 *__restrict__ A = reinterpret_cast<const uint4 *>(a.asr);
+    const uint4 *__restrict__ B = reinterpret_cast<const uint4 *>(a.audio);
+    const int64_t n = a.n_rows;
+    const int64_t stride = int64_t(gridDim.x) * kScoreWarps * kRowsPerIter;
+
+    for (int64_t base = (int64_t(blockIdx.x) * kScoreWarps + warp) * kRowsPerIter; base < n; base += stride) {
+        uint4 ca[U][3], cb[U][3];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            int64_t r = base + u * RW + sub;
+            r = r < n ? r : n - 1;                        // clamp: tail rows are not stored
+            const uint4 *pa = A + r * CPR + g;
+            const uint4 *pb = B + r * CPR + g;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) { ca[u][j] = ldg_stream(pa + G * j); cb[u][j] = ldg_stream(pb + G * j); }
+        }
+        uint32_t fl[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t row = base + u * RW + sub;
+            fl[u] = a.flags[row < n ? row : n - 1];
+        }
+        // Keep all 6U loads in flight: nothing below may be scheduled between the loads above.
+#pragma unroll
+        for (int u = 0; u < U; ++u) { keep_live(ca[u]); keep_live(cb[u]); }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t row = base + u * RW + sub;
+            const uint32_t cls = (fl[u] >> 2) & 3u;
+            float sa = 0.f, sb = 0.f;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) { sa = dot_chunk<DT>(ca[u][j], q, j, sa); sb = dot_chunk<DT>(cb[u][j], q, j, sb); }
+            sa = group_sum<DT>(sa);
+            sb = group_sum<DT>(sb);
+            // fp32 products and sum rounded separately, as numpy evaluates `wa * s_asr + wb * s_cap`
+            // on float32 scalars (no fused multiply-add)
+            const float wa = (cls & 2u) ? ((cls & 1u) ? cw[3][0] : cw[2][0]) : ((cls & 1u) ? cw[1][0] : cw[0][0]);
+            const float wb = (cls & 2u) ? ((cls & 1u) ? cw[3][1] : cw[2][1]) : ((cls & 1u) ? cw[1][1] : cw[0][1]);
+            float f = __fadd_rn(__fmul_rn(wa, sa), __fmul_rn(wb, sb));
+            if (!finite) f = __int_as_float(0x7fc00000);  // NaN/Inf query: every score is NaN
+            if (g == 0 && row < n) a.out[row] = f;
+        }
+    }
+}
+
+template <int DT, int U, int MB>
+static void launch(const ScoreAllArgs &a, int sm_count, cudaStream_t s) {
+    using TR = RowTraits<DT>;
+    const int64_t rows_per_cta = int64_t(kScoreWarps) * U * TR::RW;
+    int64_t grid = (a.n_rows + rows_per_cta - 1) / rows_per_cta;
+    if (grid > int64_t(sm_count) * MB) grid = int64_t(sm_count) * MB;   // persistent: every SM full, once
+    if (grid < 1) grid = 1;
+    score_all_kernel<DT, U, MB><<<int(grid), kScoreThreads, 0, s>>>(a);
+}
+
+void launch_score_all(const ScoreAllArgs &a, int sm_count, cudaStream_t s) {
+    if (a.dtype == CAB_BF16) launch<CAB_BF16, 2, 2>(a, sm_count, s);
+    else launch<CAB_F32, 4, 1>(a, sm_count, s);
+}
+
+}  // namespace cab

@@ -28,6 +28,7 @@ import numpy as np
 
 from . import query_weights
 from .index import SegmentIndex
+from .segment_table import SegmentRecord, SegmentTable
 
 TOP_K = 10          # audio_search.py:699
 THRESHOLD = 0.1     # audio_search.py:672
@@ -73,8 +74,44 @@ class _DeviceLibrary:
         self.index: SegmentIndex | None = None
         self.n_synced = 0
         self._last_seg = None
+        self._table_generation = -1
 
-    def sync(self, segments: List[Dict]) -> SegmentIndex:
+    def _sync_table(self, table: SegmentTable) -> SegmentIndex:
+        """Columnar library: the table hands over the embeddings of its new rows once and
+        forgets them; rows loaded from a file are in the index already (load_library)."""
+        fresh = table is not self._last_seg or table.generation != self._table_generation
+        if self.index is None:
+            self.index = SegmentIndex(self.dtype, capacity=max(1024, len(table)), device=self.device)
+        elif fresh:
+            self.index.clear()
+        if fresh:
+            self._last_seg, self._table_generation = table, table.generation
+            table.bind_index(self.index)
+        if table.n_pending:
+            row0, asr, audio, flags = table.drain_pending()
+            if row0 != len(self.index):
+                raise RuntimeError(f"segment table and device index are out of step "
+                                   f"(table rows before the new ones: {row0}, index rows: {len(self.index)})")
+            self.index.append(asr, audio, flags)                      # ValueError on NaN/Inf
+        if len(self.index) != len(table):
+            raise RuntimeError(f"segment table has {len(table)} rows, the device index {len(self.index)}")
+        self.n_synced = len(table)
+        return self.index
+
+    def adopt(self, index: SegmentIndex, table: SegmentTable) -> None:
+        """Take a loaded (index, table) pair as the synced state."""
+        if len(index) != len(table):
+            raise ValueError(f"index file has {len(index)} rows, segment table {len(table)}")
+        if self.index is not None:
+            self.index.close()
+        self.index, self.dtype = index, index.dtype
+        self._last_seg, self._table_generation = table, table.generation
+        table.bind_index(index)
+        self.n_synced = len(table)
+
+    def sync(self, segments) -> SegmentIndex:
+        if isinstance(segments, SegmentTable):
+            return self._sync_table(segments)
         if self.index is None:
             self.index = SegmentIndex(self.dtype, capacity=max(1024, len(segments)), device=self.device)
         # the reference only ever appends; if the list was replaced or shrunk, rebuild
@@ -121,8 +158,7 @@ def _b200_search_with_fusion(self, query: str) -> Tuple[List[Dict], Dict]:
         effective_audio_weight /= total_weight
         fusion_score = (effective_asr_weight * asr_similarity +
                         effective_audio_weight * audio_similarity)    # :667-670
-        results.append({
-            **segment,
+        scores = {
             "asr_similarity": asr_similarity,
             "audio_similarity": audio_similarity,
             "fusion_score": fusion_score,
@@ -130,7 +166,10 @@ def _b200_search_with_fusion(self, query: str) -> Tuple[List[Dict], Dict]:
             "effective_audio_weight": effective_audio_weight,
             "query_asr_weight": asr_weight,
             "query_audio_weight": audio_weight,
-        })
+        }
+        # :673-682; a columnar record keeps audio_data / embeddings lazy until the UI reads them
+        results.append(segment.with_fields(**scores) if isinstance(segment, SegmentRecord)
+                       else {**segment, **scores})
     processing_time = time.time() - start_time
     self.stats["search_pipeline"].update(processing_time, success=len(results) > 0)      # :688-689
     weight_info = {"asr_weight": asr_weight, "audio_weight": audio_weight,
@@ -138,12 +177,41 @@ def _b200_search_with_fusion(self, query: str) -> Tuple[List[Dict], Dict]:
     return results, weight_info
 
 
-def accelerate(search_system, dtype: str = "fp32", device: int = 0):
+def accelerate(search_system, dtype: str = "fp32", device: int = 0, columnar: bool = False):
     """Replace `search_system.search_with_fusion` (a reference DualPipelineAudioSearch, or any
-    object with the same attributes) by the B200 path.  Returns the same object."""
+    object with the same attributes) by the B200 path.  Returns the same object.
+
+    `columnar=True` also replaces the `audio_segments` list by a SegmentTable holding the same
+    records (the app's `audio_segments.extend(segments)`, :797, keeps working): embeddings then
+    live only in HBM and the library can be saved with `save_library`."""
     search_system._cab_library = _DeviceLibrary(dtype, device)
+    if columnar and not isinstance(search_system.audio_segments, SegmentTable):
+        search_system.audio_segments = SegmentTable.from_segments(search_system.audio_segments)
     search_system.search_with_fusion = types.MethodType(_b200_search_with_fusion, search_system)
     return search_system
+
+
+def save_library(search_system, path: str, audio: bool = True) -> None:
+    """Persist an accelerated engine's library: `path` (embeddings + flags as resident in HBM,
+    SegmentIndex.save), `path + '.meta'` (columnar records) and `path + '.meta.audio'` (samples).
+    The reference has no counterpart: its library dies with the Streamlit session (:708-711)."""
+    if not search_system.audio_segments:
+        raise ValueError("the library is empty")
+    index = search_system._cab_library.sync(search_system.audio_segments)
+    segments = search_system.audio_segments
+    table = segments if isinstance(segments, SegmentTable) else SegmentTable.from_segments(segments)
+    index.save(path)
+    table.save(path + ".meta", audio=audio)
+
+
+def load_library(search_system, path: str, device: int | None = None) -> None:
+    """Inverse of save_library: `audio_segments` becomes a memory-mapped SegmentTable, the
+    embeddings go straight from the file to HBM; no per-segment Python work."""
+    lib = search_system._cab_library
+    table = SegmentTable.load(path + ".meta")
+    index = SegmentIndex.load(path, device=lib.device if device is None else device)
+    lib.adopt(index, table)
+    search_system.audio_segments = table
 
 
 class DualPipelineAudioSearch:
@@ -161,6 +229,13 @@ class DualPipelineAudioSearch:
         return query_weights.analyze_query_for_weights(query)
 
     search_with_fusion = _b200_search_with_fusion
+
+    # -- beyond the reference: a library that outlives the session ---
+    def save_library(self, path: str, audio: bool = True) -> None:
+        save_library(self, path, audio=audio)
+
+    def load_library(self, path: str) -> None:
+        load_library(self, path)
 
     # -- beyond the reference: many queries per call (BASELINE configs 3-5) ----------------------
     def search_batch(self, query_vectors, asr_weights, audio_weights, k: int = TOP_K,

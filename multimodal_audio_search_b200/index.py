@@ -226,6 +226,39 @@ class SegmentIndex:
                                    float(threshold), _PATHS[path])
         return SearchResult(*out)
 
+    # -- legacy modes: every segment's fused score ---------------------------------------------
+    def score_all(self, queries, class_weights):
+        """All-N fused similarities, no threshold / top-k (the earlier engine's
+        `UnifiedAudioSearch.search`, previous_iterations/streamlit_app.py:173-223).
+        class_weights: [4][2] (or [Q][4][2]) = {w_asr, w_audio} per row weight class (bits 2-3 of
+        the row's flag byte).  numpy queries -> numpy float32 [Q, N]; CUDA tensor -> CUDA tensor."""
+        n = len(self)
+        dev_in = _is_torch_cuda(queries)
+        if dev_in:
+            import torch
+            q = queries if queries.dim() == 2 else queries.unsqueeze(0)
+            if q.dtype != torch.float32 or q.shape[1] != self.dim or not q.is_contiguous():
+                raise ValueError(f"expected contiguous float32 [n x {self.dim}] queries")
+            nq = q.shape[0]
+        else:
+            q = _np_f32(np.atleast_2d(queries), self.dim)
+            nq = q.shape[0]
+        cw = np.asarray(class_weights, dtype=np.float32)
+        if cw.shape == (4, 2):
+            cw = np.broadcast_to(cw, (nq, 4, 2))
+        if cw.shape != (nq, 4, 2):
+            raise ValueError("class_weights must be [4][2] or [n_queries][4][2]")
+        cw = np.ascontiguousarray(cw)
+        if dev_in:
+            out = torch.empty((nq, n), dtype=torch.float32, device=q.device)
+            N.check(self._lib.cab_score_all(self._h, C.c_void_p(q.data_ptr()), N.CAB_DEVICE, nq, _ptr(cw),
+                                            C.c_void_p(out.data_ptr()), N.CAB_DEVICE, self._stream()), self._h)
+            return out
+        out = np.empty((nq, n), dtype=np.float32)
+        N.check(self._lib.cab_score_all(self._h, _ptr(q), N.CAB_HOST, nq, _ptr(cw), _ptr(out),
+                                        N.CAB_HOST, None), self._h)
+        return out
+
     # -- sharded search (corpus split by segment over ranks) -----------------------------------
     def search_candidates(self, queries, w_asr=0.5, w_audio=0.5, k: int = 10,
                           threshold: float = 0.1, path: str = "auto"):

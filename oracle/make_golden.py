@@ -16,6 +16,9 @@ Fixtures (all outputs come from the reference's own `search_with_fusion` /
                       vectors incl. None / zero / scaled rows) + the reference's answers.
   flag_cases.json     libraries where `*_success` and "embedding present" disagree.
   query_weights.json  query strings -> (asr_weight, audio_weight, analysis).
+  legacy_scores.npz   the earlier engine (`previous_iterations/streamlit_app.py:173-223`,
+                      `UnifiedAudioSearch.search`): all-N similarity vectors for the strategies
+                      asr_only / caption_only / adaptive on seeded libraries.
 """
 from __future__ import annotations
 
@@ -30,6 +33,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from multimodal_audio_search_b200 import synth  # noqa: E402
+from oracle import numpy_oracle as no  # noqa: E402
 from oracle import reference_shim as rs  # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden")
@@ -218,6 +222,33 @@ def query_weights():
     print("weights", len(out))
 
 
+LEGACY_CASES = [
+    # name, seed, n_rows, plants per query, partial (some embeddings None)
+    ("legacy_500", 77, 500, 10, True),
+    ("legacy_full_257", 78, 257, 6, False),
+]
+LEGACY_QUERIES = 2
+
+
+def legacy_scores():
+    out = {}
+    meta = []
+    for name, seed, n, plants, partial in LEGACY_CASES:
+        a, b, f, _ = synth.library(seed, n, LEGACY_QUERIES, plants, partial)
+        q = synth.raw_queries(seed, 0, LEGACY_QUERIES)
+        has_a, has_b = (f & 1).astype(bool), (f & 2).astype(bool)
+        good = no.legacy_good_speech(seed, n)
+        db = rs.legacy_database(a, b, has_a, has_b, good)
+        for qi in range(LEGACY_QUERIES):
+            for strategy in ("asr_only", "caption_only", "adaptive"):
+                sims = rs.legacy_search(f"query {qi}", q[qi], db, strategy)
+                out[f"{name}/{qi}/{strategy}"] = np.asarray(sims)
+        meta.append({"name": name, "seed": seed, "n_rows": n, "plants": plants, "partial": partial,
+                     "n_queries": LEGACY_QUERIES})
+    np.savez_compressed(os.path.join(GOLD, "legacy_scores.npz"), meta=json.dumps(meta), **out)
+    print("legacy", len(out))
+
+
 if __name__ == "__main__":
     if not rs.available():
         sys.exit("reference not present: goldens can only be minted in the build container")
@@ -226,3 +257,5 @@ if __name__ == "__main__":
     known_answer()
     flag_cases()
     search_cases()
+    if rs.legacy_available():
+        legacy_scores()

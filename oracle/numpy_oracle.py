@@ -159,3 +159,47 @@ def search_prenormalized(qn, asr_n, audio_n, flags, w_asr: float, w_audio: float
         passing = passing[fusion[passing] >= kth]
     order = passing[np.argsort(-fusion[passing], kind="stable")][:k]
     return order.astype(np.int64), fusion[order], sa[order], sb[order]
+
+
+# ---- the earlier engine's modes (previous_iterations/streamlit_app.py:173-223) --------------------
+LEGACY_CLASS_WEIGHTS = {
+    # strategy -> {w_asr, w_caption} per row weight class; class 1 = len(transcript.strip()) > 10 (:216)
+    "asr_only": ((1.0, 0.0),) * 4,                                        # :188-193
+    "caption_only": ((0.0, 1.0),) * 4,                                    # :195-200
+    "adaptive": ((0.2, 0.8), (0.7, 0.3), (0.2, 0.8), (0.2, 0.8)),         # :217 / :219
+}
+
+
+def legacy_good_speech(seed: int, n: int) -> np.ndarray:
+    """Synthetic libraries: which items carry a transcript longer than 10 characters (:216).
+    Integer hash, so fixtures and tests regenerate it from the seed."""
+    i = np.arange(n, dtype=np.uint64)
+    h = (i * np.uint64(2654435761) + np.uint64(seed) * np.uint64(40503)) & np.uint64(0xFFFFFFFF)
+    return ((h >> np.uint64(13)) & np.uint64(1)).astype(bool)
+
+
+def legacy_scores(q, asr_rows, caption_rows, has_asr, has_caption, row_class, strategy: str = "adaptive") -> np.ndarray:
+    """`UnifiedAudioSearch.search` for every item: float32 (N,) similarities, no threshold.
+    A `None` embedding gives 0.0 (:203-210).  `w * sim` multiplies a Python float with a
+    numpy float32 scalar: float32 arithmetic under NumPy >= 2 promotion (the weight is rounded to
+    fp32, each product and the sum are rounded separately); the single-corpus modes return the
+    cosine itself."""
+    sa = cosine_rows(q, asr_rows, np.asarray(has_asr, dtype=bool))
+    sb = cosine_rows(q, caption_rows, np.asarray(has_caption, dtype=bool))
+    if strategy == "asr_only":
+        return sa
+    if strategy == "caption_only":
+        return sb
+    table = np.asarray(LEGACY_CLASS_WEIGHTS[strategy], dtype=np.float32)
+    cls = np.asarray(row_class, dtype=np.int64) & 3
+    return (table[cls, 0] * sa + table[cls, 1] * sb).astype(np.float32)
+
+
+def class_weight_scores(q, asr_rows, caption_rows, has_asr, has_caption, row_class, class_weights) -> np.ndarray:
+    """The general form the engine computes (include/cab.h, cab_score_all): fp32
+    `w[c][0] * s_asr + w[c][1] * s_caption` with each operation rounded separately."""
+    sa = cosine_rows(q, asr_rows, np.asarray(has_asr, dtype=bool))
+    sb = cosine_rows(q, caption_rows, np.asarray(has_caption, dtype=bool))
+    table = np.asarray(class_weights, dtype=np.float32).reshape(4, 2)
+    cls = np.asarray(row_class, dtype=np.int64) & 3
+    return (table[cls, 0] * sa + table[cls, 1] * sb).astype(np.float32)

@@ -51,6 +51,68 @@ def load():
     return mod
 
 
+LEGACY_FILE = os.path.join(os.path.dirname(REFERENCE_FILE), "previous_iterations", "streamlit_app.py")
+_legacy = None
+
+
+def legacy_available() -> bool:
+    return os.path.exists(LEGACY_FILE)
+
+
+def load_legacy():
+    """Import the reference's earlier engine (previous_iterations/streamlit_app.py) for its
+    `UnifiedAudioSearch.search` (:173-223).  Its class body applies `@st.cache_resource`, so the
+    streamlit stub gets a pass-through decorator; `main()` is guarded by `__name__`."""
+    global _legacy
+    if _legacy is not None:
+        return _legacy
+    if not legacy_available():
+        raise FileNotFoundError(LEGACY_FILE)
+    load()                                          # installs the stub modules
+    st = sys.modules["streamlit"]
+    if not hasattr(st, "cache_resource"):
+        st.cache_resource = lambda f=None, **_kw: f if f is not None else (lambda g: g)
+    spec = importlib.util.spec_from_file_location("reference_legacy_app", LEGACY_FILE)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    _legacy = mod
+    return mod
+
+
+class ListEmbedder:
+    """The earlier engine calls `sentence_model.encode([text])[0]` (:184)."""
+
+    def __init__(self, table: dict[str, np.ndarray]):
+        self.table = {k: np.asarray(v, dtype=np.float32) for k, v in table.items()}
+
+    def encode(self, texts, **_kw):
+        return np.stack([self.table[t] for t in texts])
+
+
+def legacy_database(asr, caption, has_asr, has_caption, good_speech) -> list[dict]:
+    """The earlier engine's database items (streamlit_app.py:322-336): embeddings or None, and a
+    transcript whose stripped length decides the adaptive weights (:216)."""
+    db = []
+    for i in range(len(has_asr)):
+        db.append({
+            "filename": "synthetic.wav", "chunk_id": i, "start_time": 10.0 * i, "end_time": 10.0 * i + 10.0,
+            "asr_embedding": np.asarray(asr[i], dtype=np.float32) if has_asr[i] else None,
+            "caption_embedding": np.asarray(caption[i], dtype=np.float32) if has_caption[i] else None,
+            "asr_transcription": ("a clearly spoken sentence %d" % i) if good_speech[i] else " uh ",
+            "audio_caption": "some sound",
+            "has_asr": bool(has_asr[i]), "has_caption": bool(has_caption[i]),
+        })
+    return db
+
+
+def legacy_search(query_text: str, query_vec, database, strategy: str) -> np.ndarray:
+    """Run the reference's own `UnifiedAudioSearch.search` on `database`."""
+    mod = load_legacy()
+    eng = mod.UnifiedAudioSearch()
+    eng.sentence_model = ListEmbedder({query_text: query_vec})
+    return eng.search(query_text, database, strategy)
+
+
 class FakeEmbedder:
     """Stands in for SentenceTransformer: `.encode(text)` returns the vector registered for it."""
 

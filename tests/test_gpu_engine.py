@@ -86,3 +86,66 @@ def test_replaced_library_is_resynced():
     with pytest.raises(ValueError):
         eng.audio_segments.append({**eng.audio_segments[0], "asr_embedding": np.ones(100, np.float32)})
         eng.search_with_fusion("zzz")
+
+
+def test_columnar_library_gives_the_same_results_and_survives_a_session(search_cases, tmp_path):
+    """SegmentTable instead of the list of dicts (8(f) rank 3) + save/load (rank 1): same
+    `search_with_fusion` return value; lazy audio_data / embeddings resolve to the right rows."""
+    from multimodal_audio_search_b200 import SegmentRecord, SegmentTable
+    case = search_cases[1]
+    a, b, f, _ = synth.library(case["seed"], case["n_rows"], case["n_queries"], case["plants"], case["partial"])
+    q = synth.raw_queries(case["seed"], 0, case["n_queries"])
+    embedder = FakeEmbedder({r["text"]: q[r["qi"]] for r in case["queries"]})
+    segs = segments_from_arrays(a, b, f)
+    for i, s in enumerate(segs):
+        s["audio_data"] = np.full(8, i, dtype=np.float32)
+
+    eng = DualPipelineAudioSearch(text_embedder=embedder)
+    eng.audio_segments = SegmentTable()
+    half = len(segs) // 2
+    eng.audio_segments.extend(segs[:half], file="a.wav")
+    eng.search_with_fusion(case["queries"][0]["text"])
+    eng.audio_segments.extend(segs[half:], file="b.wav")
+    assert eng.audio_segments.n_pending == len(segs) - half
+    for rec in case["queries"]:
+        results, info = eng.search_with_fusion(rec["text"])
+        assert all(isinstance(r, SegmentRecord) for r in results)
+        _check([{k: v for k, v in r.items() if k != "file"} for r in results], info, rec)
+        for r in results:
+            row = int(r["segment_id"][4:])
+            assert r["file"] == ("a.wav" if row < half else "b.wav")
+            assert r["audio_data"][0] == row
+            for key, src in (("asr_embedding", a), ("audio_embedding", b)):
+                e = r[key]                                    # read back from HBM, L2-normalised
+                if not np.any(src[row]):
+                    assert e is None
+                else:
+                    assert np.allclose(e, src[row] / np.linalg.norm(src[row]), atol=1e-6)
+    assert eng.audio_segments.n_pending == 0
+
+    path = str(tmp_path / "library.cab")
+    eng.save_library(path)
+    fresh = DualPipelineAudioSearch(text_embedder=embedder)
+    fresh.load_library(path)
+    assert len(fresh.audio_segments) == len(segs)
+    for rec in case["queries"]:
+        results, info = fresh.search_with_fusion(rec["text"])
+        _check([{k: v for k, v in r.items() if k != "file"} for r in results], info, rec)
+    extra = segments_from_arrays(a[:3], b[:3], f[:3])
+    fresh.audio_segments.extend(extra)                        # a loaded library keeps growing
+    fresh.search_with_fusion(case["queries"][0]["text"])
+    assert len(fresh._cab_library.index) == len(segs) + 3
+
+    # a list-based engine can be saved too, and accelerate(columnar=True) converts in place
+    listy = DualPipelineAudioSearch(text_embedder=embedder)
+    listy.audio_segments.extend(segs)
+    listy.save_library(str(tmp_path / "listy.cab"))
+    again = DualPipelineAudioSearch(text_embedder=embedder)
+    again.load_library(str(tmp_path / "listy.cab"))
+    rec = case["queries"][0]
+    results, info = again.search_with_fusion(rec["text"])
+    _check([{k: v for k, v in r.items() if k != "file"} for r in results], info, rec)
+    conv = accelerate(listy, columnar=True)
+    assert isinstance(conv.audio_segments, SegmentTable)
+    results, info = conv.search_with_fusion(rec["text"])
+    _check([{k: v for k, v in r.items() if k != "file"} for r in results], info, rec)
