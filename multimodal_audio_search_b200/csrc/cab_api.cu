@@ -49,7 +49,7 @@ struct cab_index {
     uint8_t *d_out = nullptr;      size_t d_out_bytes = 0;  // packed outputs
     uint8_t *d_gemm_ws = nullptr;  size_t d_gemm_ws_bytes = 0;
     int *d_nonfinite = nullptr;
-    unsigned int *d_counters = nullptr;     // [64] GEMV chunk tickets (zero between searches)
+    unsigned int *d_counters = nullptr;     // [0..63] GEMV chunk tickets, [64..65] score_all tickets (zero between launches)
     // pinned host staging
     uint8_t *h_in = nullptr;  size_t h_in_bytes = 0;
     uint8_t *h_out = nullptr; size_t h_out_bytes = 0;
@@ -175,8 +175,8 @@ int cab_index_create(int dim, int dtype, int64_t capacity_rows, int device, cab_
     if (e == cudaSuccess) e = cudaMemset(idx->d_nonfinite, 0, sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&idx->d_host_done, sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(idx->d_host_done, 0, sizeof(unsigned int));
-    if (e == cudaSuccess) e = cudaMalloc(&idx->d_counters, 64 * sizeof(unsigned int));
-    if (e == cudaSuccess) e = cudaMemset(idx->d_counters, 0, 64 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc(&idx->d_counters, 128 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(idx->d_counters, 0, 128 * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&idx->ev_in, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreate(&idx->ev_t0);
     if (e == cudaSuccess) e = cudaEventCreate(&idx->ev_t1);
@@ -869,6 +869,10 @@ int cab_score_all(cab_index *idx, const float *queries, int queries_loc, int n_q
     ScoreAllArgs a{};
     a.asr = idx->asr; a.audio = idx->audio; a.flags = idx->flags; a.n_rows = idx->size; a.dtype = idx->dtype;
     a.nonfinite = host_out ? idx->d_nonfinite : nullptr;     // device results: a bad query gives NaN scores
+    a.work_counters = idx->d_counters + 64;
+    a.chunk_rows = idx->opt_chunk_rows ? int(idx->opt_chunk_rows) : (idx->dtype == CAB_BF16 ? 64 : 32);
+    idx->timed = false;
+    if (idx->opt_time_kernels) CU(idx, cudaEventRecord(idx->ev_t0, s));
     for (int q = 0; q < n_queries; ++q) {
         if (queries_loc == CAB_HOST) { a.use_inline_query = 1; memcpy(a.q, queries + size_t(q) * CAB_DIM, sizeof a.q); }
         else { a.use_inline_query = 0; a.query = queries + size_t(q) * CAB_DIM; }
@@ -877,6 +881,7 @@ int cab_score_all(cab_index *idx, const float *queries, int queries_loc, int n_q
         launch_score_all(a, idx->sm_count, s);
         idx->launches += 1;
     }
+    if (idx->opt_time_kernels) { CU(idx, cudaEventRecord(idx->ev_t1, s)); idx->timed = true; }
     CU(idx, cudaGetLastError());
     if (!host_out) {
         if (idx->opt_sync) CU(idx, cudaStreamSynchronize(s));

@@ -89,6 +89,8 @@ struct ScoreAllArgs {
     float class_w[4][2];       // {w_asr, w_audio} per weight class
     float *out;                // device [n_rows]; all NaN if the query holds NaN/Inf
     int *nonfinite;            // also set in that case (may be null)
+    unsigned int *work_counters;   // [2] chunk tickets + finished warps; zero on entry, re-armed by the kernel
+    int chunk_rows;                // rows per dynamically scheduled chunk
 };
 void launch_score_all(const ScoreAllArgs &a, int sm_count, cudaStream_t s);
 

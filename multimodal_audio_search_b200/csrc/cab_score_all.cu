@@ -14,9 +14,10 @@
 // engine's rule (audio_search.py:654-670), served by the top-k scan.
 //
 // HBM-bound like the top-k scan: 2 x 384 x sizeof(elem) bytes read + 4 bytes written per segment.
-// Same load shape (U row-steps x 2 corpora x 3 LDG.128 per lane in flight, L1-bypassing), static
-// warp-cyclic row assignment (no selection, so no load imbalance to schedule around), plain
-// butterfly reduction (the issue slots are there: ~60 of ~500 per row are used).
+// Same load shape (U row-steps x 2 corpora x 3 LDG.128 per lane in flight, L1-bypassing) and the
+// same dynamic chunk schedule as the top-k scan; plain butterfly reduction (the issue slots are
+// there: ~60 of ~500 per row are used).  A static warp-cyclic split measured 6-10 % slower
+// (profiles/r01_score_all.md).
 #include "cab_internal.h"
 #include "cab_rowdot.cuh"
 
@@ -53,9 +54,32 @@ score_all_kernel(ScoreAllArgs a) {
     const uint4 *__restrict__ A = reinterpret_cast<const uint4 *>(a.asr);
     const uint4 *__restrict__ B = reinterpret_cast<const uint4 *>(a.audio);
     const int64_t n = a.n_rows;
-    const int64_t stride = int64_t(gridDim.x) * kScoreWarps * kRowsPerIter;
+    const int64_t gwarp = int64_t(blockIdx.x) * kScoreWarps + warp;
+    const int64_t total_warps = int64_t(gridDim.x) * kScoreWarps;
 
-    for (int64_t base = (int64_t(blockIdx.x) * kScoreWarps + warp) * kRowsPerIter; base < n; base += stride) {
+    // Dynamic two-level chunk schedule, the top-k scan's (cab_gemv.cu): a warp's first chunk is
+    // its global warp id, every further one comes from an atomic ticket fetched one chunk ahead;
+    // big chunks for the bulk, quarter-size chunks for the last big chunk per warp so the tail is
+    // short.  A warp streams chunk_rows contiguous rows (96 KB over both corpora) per ticket.
+    const int kChunkRows = a.chunk_rows >= kRowsPerIter ? (a.chunk_rows / kRowsPerIter) * kRowsPerIter : kRowsPerIter;
+    const int kSmallRows = kChunkRows / 4 >= kRowsPerIter ? (kChunkRows / 4 / kRowsPerIter) * kRowsPerIter : kRowsPerIter;
+    int64_t n_big = n / kChunkRows - total_warps;
+    if (n_big < 0) n_big = 0;
+    const int64_t tail_row0 = n_big * kChunkRows;
+    const int64_t n_small = (n - tail_row0 + kSmallRows - 1) / kSmallRows;
+    const int64_t n_chunks = n_big + n_small;
+    unsigned int *counter = a.work_counters;
+    int64_t chunk = gwarp;
+    unsigned int ticket = 0;
+    if (chunk < n_chunks && lane == 0) ticket = atomicAdd(counter, 1u);
+    float keep = 0.f;                                       // this lane's pending score (row cbase + 32j + lane)
+
+    for (; chunk < n_chunks;
+         chunk = total_warps + int64_t(__shfl_sync(kFull, ticket, 0)),
+         ticket = (lane == 0 && chunk < n_chunks) ? atomicAdd(counter, 1u) : 0u)
+    for (int64_t base = chunk < n_big ? chunk * kChunkRows : tail_row0 + (chunk - n_big) * kSmallRows,
+                 cbase = base, cend = chunk < n_big ? base + kChunkRows : base + kSmallRows;
+         base < cend && base < n; base += kRowsPerIter) {
         uint4 ca[U][3], cb[U][3];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -77,7 +101,6 @@ score_all_kernel(ScoreAllArgs a) {
         for (int u = 0; u < U; ++u) { keep_live(ca[u]); keep_live(cb[u]); }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int64_t row = base + u * RW + sub;
             const uint32_t cls = (fl[u] >> 2) & 3u;
             float sa = 0.f, sb = 0.f;
 #pragma unroll
@@ -90,7 +113,32 @@ score_all_kernel(ScoreAllArgs a) {
             const float wb = (cls & 2u) ? ((cls & 1u) ? cw[3][1] : cw[2][1]) : ((cls & 1u) ? cw[1][1] : cw[0][1]);
             float f = __fadd_rn(__fmul_rn(wa, sa), __fmul_rn(wb, sb));
             if (!finite) f = __int_as_float(0x7fc00000);  // NaN/Inf query: every score is NaN
-            if (g == 0 && row < n) a.out[row] = f;
+            // Lane (r & 31) keeps the score of the chunk's r-th row, so 32 rows leave as ONE
+            // coalesced 128-byte store (full sectors) instead of 32 four-byte partial-sector ones.
+            const int r_local = int(base - cbase) + u * RW;
+            if constexpr (RW == 1) {
+                if (((r_local) & 31) == lane) keep = f;
+            } else {
+                const float other = __shfl_xor_sync(kFull, f, 16);   // the step's other row
+                if (((r_local) & 31) == lane) keep = sub == 0 ? f : other;
+                if (((r_local + 1) & 31) == lane) keep = sub == 0 ? other : f;
+            }
+        }
+        const int64_t done = base + kRowsPerIter;                    // rows of this chunk scored so far end here
+        const int64_t lim = cend < n ? cend : n;
+        if (((done - cbase) & 31) == 0 || done >= lim) {
+            const int64_t sbase = cbase + ((done - 1 - cbase) & ~int64_t(31));
+            const int64_t row = sbase + lane;
+            if (row < done && row < lim) a.out[row] = keep;
+        }
+    }
+    // The last warp to run out of chunks re-arms the counters for the next launch (every warp's
+    // last ticket fetch precedes its arrival here, so nobody touches the ticket counter after).
+    if (lane == 0) {
+        __threadfence();
+        if (atomicAdd(a.work_counters + 1, 1u) == unsigned(total_warps - 1)) {
+            a.work_counters[0] = 0u;
+            a.work_counters[1] = 0u;
         }
     }
 }

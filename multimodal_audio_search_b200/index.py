@@ -227,11 +227,13 @@ class SegmentIndex:
         return SearchResult(*out)
 
     # -- legacy modes: every segment's fused score ---------------------------------------------
-    def score_all(self, queries, class_weights):
+    def score_all(self, queries, class_weights, out=None):
         """All-N fused similarities, no threshold / top-k (the earlier engine's
         `UnifiedAudioSearch.search`, previous_iterations/streamlit_app.py:173-223).
         class_weights: [4][2] (or [Q][4][2]) = {w_asr, w_audio} per row weight class (bits 2-3 of
-        the row's flag byte).  numpy queries -> numpy float32 [Q, N]; CUDA tensor -> CUDA tensor."""
+        the row's flag byte).  numpy queries -> numpy float32 [Q, N]; CUDA tensor -> CUDA tensor.
+        `out`: optional C-contiguous float32 [Q, N] numpy array to fill (host results only); a
+        view of page-locked memory (`pinned_scores`) makes the copy back run at PCIe speed."""
         n = len(self)
         dev_in = _is_torch_cuda(queries)
         if dev_in:
@@ -254,10 +256,26 @@ class SegmentIndex:
             N.check(self._lib.cab_score_all(self._h, C.c_void_p(q.data_ptr()), N.CAB_DEVICE, nq, _ptr(cw),
                                             C.c_void_p(out.data_ptr()), N.CAB_DEVICE, self._stream()), self._h)
             return out
-        out = np.empty((nq, n), dtype=np.float32)
+        if out is None:
+            out = np.empty((nq, n), dtype=np.float32)
+        elif not (isinstance(out, np.ndarray) and out.dtype == np.float32 and out.shape == (nq, n)
+                  and out.flags.c_contiguous and out.flags.writeable):
+            raise ValueError(f"out must be a writable C-contiguous float32 array of shape {(nq, n)}")
         N.check(self._lib.cab_score_all(self._h, _ptr(q), N.CAB_HOST, nq, _ptr(cw), _ptr(out),
                                         N.CAB_HOST, None), self._h)
         return out
+
+    def pinned_scores(self, n_queries: int = 1) -> np.ndarray:
+        """A page-locked float32 [n_queries, len(self)] numpy view to pass as `score_all(out=)`;
+        the buffer is owned by the index and reused (grown geometrically) between calls."""
+        import torch
+        need = int(n_queries) * len(self)
+        buf = getattr(self, "_pinned", None)
+        if buf is None or buf.numel() < need:
+            buf = torch.empty(max(need, 2 * (buf.numel() if buf is not None else 0), 1), dtype=torch.float32,
+                              pin_memory=True)
+            self._pinned = buf
+        return buf[:need].view(int(n_queries), len(self)).numpy()
 
     # -- sharded search (corpus split by segment over ranks) -----------------------------------
     def search_candidates(self, queries, w_asr=0.5, w_audio=0.5, k: int = 10,

@@ -95,7 +95,8 @@ def _b200_search(self, query_text, audio_database, strategy="adaptive"):
         return np.array([])                                                   # np.array([]) of :223
     index = self._cab_database.sync(audio_database)
     weights = CLASS_WEIGHTS.get(strategy, CLASS_WEIGHTS["adaptive"])          # the `else:` of :202
-    return index.score_all(query_embedding[None, :], weights)[0].astype(np.float64)
+    scores = index.score_all(query_embedding[None, :], weights, out=index.pinned_scores(1))
+    return scores[0].astype(np.float64)       # an owned float64 vector, like np.array(similarities)
 
 
 def accelerate_legacy(system, dtype: str = "fp32", device: int = 0):

@@ -95,6 +95,11 @@ def test_device_tensors_nan_query_and_empty_index():
     assert res.count.shape == (2,)
     with pytest.raises(ValueError):
         idx.score_all(q, np.zeros((3, 2), np.float32))
+    pinned = idx.pinned_scores(2)                                            # page-locked output buffer
+    assert idx.score_all(q, no.LEGACY_CLASS_WEIGHTS["adaptive"], out=pinned) is pinned
+    assert np.array_equal(pinned, host)
+    with pytest.raises(ValueError, match="out must be"):
+        idx.score_all(q, no.LEGACY_CLASS_WEIGHTS["adaptive"], out=np.zeros((2, n), np.float64))
     idx.close()
 
 
