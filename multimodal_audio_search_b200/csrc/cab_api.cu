@@ -57,6 +57,7 @@ struct cab_index {
     float *d_rows = nullptr;  size_t d_rows_bytes = 0;   // raw-row device staging (append)
     uint8_t *d_scores = nullptr; size_t d_scores_bytes = 0;   // cab_score_all with host output
     cudaEvent_t ev_in = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    cudaEvent_t ev_slot[2] = {nullptr, nullptr};     // append staging slots
     bool ev_in_pending = false, timed = false;
     // options
     GemvConfig gemv{0, 0, 0, 0};
@@ -208,6 +209,7 @@ int cab_index_destroy(cab_index *idx) {
     if (idx->ev_in) cudaEventDestroy(idx->ev_in);
     if (idx->ev_t0) cudaEventDestroy(idx->ev_t0);
     if (idx->ev_t1) cudaEventDestroy(idx->ev_t1);
+    for (cudaEvent_t e : idx->ev_slot) if (e) cudaEventDestroy(e);
     if (idx->own_stream) cudaStreamDestroy(idx->own_stream);
     cudaGetLastError();
     delete idx;
@@ -272,25 +274,33 @@ int cab_index_append(cab_index *idx, const float *asr_rows, const float *audio_r
         if (flags) CU(idx, cudaMemcpyAsync(idx->flags + dst0, flags, size_t(n_rows), cudaMemcpyDeviceToDevice, s));
         else CU(idx, cudaMemsetAsync(idx->flags + dst0, 3, size_t(n_rows), s));
     } else {
-        const int64_t chunk = 16384;                                   // rows per staging step (2 x 24 MB)
+        // Two staging slots (pinned host + device), used alternately: the CPU copies chunk i+1 into
+        // its pinned slot while the copy engine and the normalise kernels work on chunk i.
+        const int64_t chunk = 8192;                                    // rows per slot (2 corpora x 12 MB)
         const size_t row_bytes = CAB_DIM * sizeof(float);
-        int rc = ensure_pinned(idx, &idx->h_rows, &idx->h_rows_bytes, 2 * size_t(chunk) * row_bytes);
+        const size_t slot_bytes = 2 * size_t(chunk) * row_bytes;
+        int rc = ensure_pinned(idx, &idx->h_rows, &idx->h_rows_bytes, 2 * slot_bytes);
         if (rc != CAB_OK) return rc;
-        if (idx->d_rows_bytes < 2 * size_t(chunk) * row_bytes) {
+        if (idx->d_rows_bytes < 2 * slot_bytes) {
             cudaFree(idx->d_rows); idx->d_rows = nullptr; idx->d_rows_bytes = 0;
-            CU(idx, cudaMalloc((void **)&idx->d_rows, 2 * size_t(chunk) * row_bytes));
-            idx->d_rows_bytes = 2 * size_t(chunk) * row_bytes;
+            CU(idx, cudaMalloc((void **)&idx->d_rows, 2 * slot_bytes));
+            idx->d_rows_bytes = 2 * slot_bytes;
         }
-        for (int64_t r = 0; r < n_rows; r += chunk) {
+        for (int i = 0; i < 2; ++i)
+            if (!idx->ev_slot[i]) CU(idx, cudaEventCreateWithFlags(&idx->ev_slot[i], cudaEventDisableTiming));
+        int64_t step = 0;
+        for (int64_t r = 0; r < n_rows; r += chunk, ++step) {
+            const int slot = int(step & 1);
             const int64_t m = std::min(chunk, n_rows - r);
-            float *ha = reinterpret_cast<float *>(idx->h_rows), *hb = ha + chunk * CAB_DIM;
-            float *da = idx->d_rows, *db = da + chunk * CAB_DIM;
+            float *ha = reinterpret_cast<float *>(idx->h_rows + slot * slot_bytes), *hb = ha + chunk * CAB_DIM;
+            float *da = idx->d_rows + slot * (slot_bytes / sizeof(float)), *db = da + chunk * CAB_DIM;
+            if (step >= 2) CU(idx, cudaEventSynchronize(idx->ev_slot[slot]));     // the slot's previous chunk is consumed
             if (asr_rows) { memcpy(ha, asr_rows + r * CAB_DIM, size_t(m) * row_bytes); CU(idx, cudaMemcpyAsync(da, ha, size_t(m) * row_bytes, cudaMemcpyHostToDevice, s)); }
             if (audio_rows) { memcpy(hb, audio_rows + r * CAB_DIM, size_t(m) * row_bytes); CU(idx, cudaMemcpyAsync(db, hb, size_t(m) * row_bytes, cudaMemcpyHostToDevice, s)); }
             launch_normalize_rows(asr_rows ? da : nullptr, idx->asr, idx->dtype, dst0 + r, m, idx->d_nonfinite, s);
             launch_normalize_rows(audio_rows ? db : nullptr, idx->audio, idx->dtype, dst0 + r, m, idx->d_nonfinite, s);
             idx->launches += 2;
-            CU(idx, cudaStreamSynchronize(s));                         // staging buffers are reused
+            CU(idx, cudaEventRecord(idx->ev_slot[slot], s));
         }
         if (flags) CU(idx, cudaMemcpyAsync(idx->flags + dst0, flags, size_t(n_rows), cudaMemcpyHostToDevice, s));
         else CU(idx, cudaMemsetAsync(idx->flags + dst0, 3, size_t(n_rows), s));

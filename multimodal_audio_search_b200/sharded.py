@@ -74,3 +74,30 @@ class ShardedSearcher:
             gathered = self._gathered.view((self.world,) + tuple(cands.shape))
         # the weights are already on the device (staged by search_candidates on the same handle)
         return self.index.merge_candidates(gathered, None, None, k=k, threshold=threshold, to_host=to_host)
+
+    def score_all(self, queries, class_weights, n_total: int):
+        """Legacy all-N scoring (cab_score_all) over a sharded library: every rank scores its own
+        rows, one all-gather of the score vectors (4 bytes per segment and query) gives every rank
+        the full [Q, n_total] result.  Shards are `shard_range(n_total, rank, world)`; the blocks
+        are padded to the largest shard for the collective.  Returns a tensor on the index's
+        device (numpy if the index returns numpy and world == 1)."""
+        import torch
+        import torch.distributed as dist
+        local = self.index.score_all(queries, class_weights)
+        if self.world == 1:
+            return local
+        if not torch.is_tensor(local):
+            local = torch.from_numpy(np.ascontiguousarray(local))
+        nq = local.shape[0]
+        per = -(-n_total // self.world)
+        lo, hi = shard_range(n_total, self.rank, self.world)
+        if local.shape[1] != hi - lo:
+            raise ValueError(f"rank {self.rank} holds {local.shape[1]} rows, its shard of {n_total} is {hi - lo}")
+        block = torch.zeros((nq, per), dtype=local.dtype, device=local.device)
+        block[:, :hi - lo] = local
+        gathered = torch.empty((self.world * nq, per), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(gathered, block, group=self.group)
+        # [world, Q, per] -> [Q, world*per]: rank r's block starts at its first global row r*per, so
+        # position == global segment index and only the tail beyond n_total is padding
+        full = gathered.view(self.world, nq, per).permute(1, 0, 2).reshape(nq, self.world * per)
+        return full[:, :n_total].contiguous()

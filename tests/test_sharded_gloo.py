@@ -42,6 +42,11 @@ class FakeShardIndex:
             out["flags"][i, :n] = self.f[o.indices]
         return torch.from_numpy(out.view(np.uint8).reshape(len(queries), k, 24))
 
+    def score_all(self, queries, class_weights):
+        cls = no.legacy_good_speech(7, self.lo + len(self.f))[self.lo:]
+        return np.stack([no.class_weight_scores(q, self.a, self.b, self.f & 1, self.f & 2, cls, class_weights)
+                         for q in queries])
+
     def merge_candidates(self, gathered, w_asr, w_audio, k, threshold, to_host):
         w_asr, w_audio = self._w          # reuse the weights of the preceding search_candidates
         c = gathered.numpy().reshape(gathered.shape[0], gathered.shape[1], k * 24).view(CANDIDATE_DTYPE)
@@ -67,6 +72,8 @@ def _worker(rank, world, port, seed, n_total, plants, nq, k, ret):
         wa = np.array([0.5, 0.3, 0.68][:nq]); wb = 1.0 - wa
         out = ShardedSearcher(idx, rank, world).search(q, wa, wb, k=k, threshold=0.1)
         ret[rank] = [(i.tolist(), f.tolist()) for i, f in out]
+        scores = ShardedSearcher(idx, rank, world).score_all(q, no.LEGACY_CLASS_WEIGHTS["adaptive"], n_total)
+        ret[f"scores{rank}"] = scores.numpy()
     finally:
         dist.destroy_process_group()
 
@@ -88,3 +95,9 @@ def test_two_rank_sharded_search_equals_single_library():
         o = no.search(q[i], a, b, f, wa[i], wb[i], k=k)
         assert ret[0][i][0] == o.indices.tolist()
         np.testing.assert_allclose(ret[0][i][1], o.fusion, atol=1e-6, rtol=0)
+    # legacy all-N scoring over the same two shards: every rank ends with the full vector
+    cls = no.legacy_good_speech(7, n_total)
+    assert ret["scores0"].shape == (nq, n_total) and np.array_equal(ret["scores0"], ret["scores1"])
+    for i in range(nq):
+        want = no.legacy_scores(q[i], a, b, f & 1, f & 2, cls, "adaptive")
+        np.testing.assert_allclose(ret["scores0"][i], want, atol=1e-6, rtol=0)
