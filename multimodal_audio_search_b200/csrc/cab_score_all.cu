@@ -73,6 +73,17 @@ score_all_kernel(ScoreAllArgs a) {
     unsigned int ticket = 0;
     if (chunk < n_chunks && lane == 0) ticket = atomicAdd(counter, 1u);
     float keep = 0.f;                                       // this lane's pending score (row cbase + 32j + lane)
+    // Which row of a step (kRowsPerIter == 4 rows) this lane carries after the transposing
+    // reduction, and the lane that carries row (lane & 3) -- see the reduction below.
+    static_assert(kRowsPerIter == 4, "the score hand-over assumes 4 rows per step");
+    int u_lane = 0;
+    {
+        int stride = G / 2, half = U / 2;
+        while (half >= 1) { if (lane & stride) u_lane += half; stride >>= 1; half >>= 1; }
+    }
+    const int my_local = u_lane * RW + sub;
+    const int want = lane & 3;                                                // row of the step this lane stores
+    const int src_lane = (want % RW) * G + (want / RW) * (G / U);             // first lane carrying that row
 
     for (; chunk < n_chunks;
          chunk = total_warps + int64_t(__shfl_sync(kFull, ticket, 0)),
@@ -90,40 +101,53 @@ score_all_kernel(ScoreAllArgs a) {
 #pragma unroll
             for (int j = 0; j < 3; ++j) { ca[u][j] = ldg_stream(pa + G * j); cb[u][j] = ldg_stream(pb + G * j); }
         }
-        uint32_t fl[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int64_t row = base + u * RW + sub;
-            fl[u] = a.flags[row < n ? row : n - 1];
-        }
+        // after the transposing reduction this lane carries row `base + my_local` of the step
+        const int64_t my_row = base + my_local;
+        const uint32_t fl = a.flags[my_row < n ? my_row : n - 1];
         // Keep all 6U loads in flight: nothing below may be scheduled between the loads above.
 #pragma unroll
         for (int u = 0; u < U; ++u) { keep_live(ca[u]); keep_live(cb[u]); }
+        float v[U][2];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const uint32_t cls = (fl[u] >> 2) & 3u;
             float sa = 0.f, sb = 0.f;
 #pragma unroll
             for (int j = 0; j < 3; ++j) { sa = dot_chunk<DT>(ca[u][j], q, j, sa); sb = dot_chunk<DT>(cb[u][j], q, j, sb); }
-            sa = group_sum<DT>(sa);
-            sb = group_sum<DT>(sb);
-            // fp32 products and sum rounded separately, as numpy evaluates `wa * s_asr + wb * s_cap`
-            // on float32 scalars (no fused multiply-add)
-            const float wa = (cls & 2u) ? ((cls & 1u) ? cw[3][0] : cw[2][0]) : ((cls & 1u) ? cw[1][0] : cw[0][0]);
-            const float wb = (cls & 2u) ? ((cls & 1u) ? cw[3][1] : cw[2][1]) : ((cls & 1u) ? cw[1][1] : cw[0][1]);
-            float f = __fadd_rn(__fmul_rn(wa, sa), __fmul_rn(wb, sb));
-            if (!finite) f = __int_as_float(0x7fc00000);  // NaN/Inf query: every score is NaN
-            // Lane (r & 31) keeps the score of the chunk's r-th row, so 32 rows leave as ONE
-            // coalesced 128-byte store (full sectors) instead of 32 four-byte partial-sector ones.
-            const int r_local = int(base - cbase) + u * RW;
-            if constexpr (RW == 1) {
-                if (((r_local) & 31) == lane) keep = f;
-            } else {
-                const float other = __shfl_xor_sync(kFull, f, 16);   // the step's other row
-                if (((r_local) & 31) == lane) keep = sub == 0 ? f : other;
-                if (((r_local + 1) & 31) == lane) keep = sub == 0 ? other : f;
-            }
+            v[u][0] = sa; v[u][1] = sb;
         }
+        // Transposing reduction (the top-k scan's): each split halves the row-steps a lane carries,
+        // 12 shuffles per 4 fp32 rows instead of 40 -- fewer instructions, less power under the cap.
+        {
+            int stride = G / 2;
+#pragma unroll
+            for (int half = U / 2; half >= 1; half >>= 1) {
+                const bool upper = (lane & stride) != 0;
+#pragma unroll
+                for (int i = 0; i < half; ++i)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const float send = upper ? v[i][c] : v[i + half][c];
+                        const float kept = upper ? v[i + half][c] : v[i][c];
+                        v[i][c] = kept + __shfl_xor_sync(kFull, send, stride);
+                    }
+                stride >>= 1;
+            }
+#pragma unroll
+            for (; stride > 0; stride >>= 1)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) v[0][c] += __shfl_xor_sync(kFull, v[0][c], stride);
+        }
+        const uint32_t cls = (fl >> 2) & 3u;
+        // fp32 products and sum rounded separately, as numpy evaluates `wa * s_asr + wb * s_cap`
+        // on float32 scalars (no fused multiply-add)
+        const float wa = (cls & 2u) ? ((cls & 1u) ? cw[3][0] : cw[2][0]) : ((cls & 1u) ? cw[1][0] : cw[0][0]);
+        const float wb = (cls & 2u) ? ((cls & 1u) ? cw[3][1] : cw[2][1]) : ((cls & 1u) ? cw[1][1] : cw[0][1]);
+        float f = __fadd_rn(__fmul_rn(wa, v[0][0]), __fmul_rn(wb, v[0][1]));
+        if (!finite) f = __int_as_float(0x7fc00000);      // NaN/Inf query: every score is NaN
+        // Lane (r & 31) keeps the score of the chunk's r-th row, so 32 rows leave as ONE coalesced
+        // 128-byte store (full sectors): the step's row (lane & 3) sits in lane src_lane.
+        const float mine = __shfl_sync(kFull, f, src_lane);
+        if ((((base - cbase) >> 2) & 7) == (lane >> 2)) keep = mine;
         const int64_t done = base + kRowsPerIter;                    // rows of this chunk scored so far end here
         const int64_t lim = cend < n ? cend : n;
         if (((done - cbase) & 31) == 0 || done >= lim) {
