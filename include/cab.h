@@ -113,6 +113,12 @@ CAB_API int cab_synth_queries(int device, uint32_t seed, int q0, int q1, float *
 CAB_API int cab_index_read_rows(cab_index *idx, int corpus /*0 asr, 1 audio*/, int64_t r0, int64_t r1,
                         float *out, int out_loc);
 
+/* Overwrite / read back the flag bytes of rows [r0, r1) (host or device buffer of r1 - r0 bytes):
+ * success bits and weight class of segments that are already in the index (e.g. assigning the
+ * legacy weight classes to a library that was ingested without them). */
+CAB_API int cab_index_write_flags(cab_index *idx, int64_t r0, int64_t r1, const uint8_t *flags, int flags_loc);
+CAB_API int cab_index_read_flags(cab_index *idx, int64_t r0, int64_t r1, uint8_t *out, int out_loc);
+
 /* ---- persistent index file (the reference keeps its library only
  * in the Streamlit session, audio_search.py:708-711, and loses it when the session ends) ---------
  * Layout (little endian): 4096-byte header {magic "CABIDX01", version, dim, dtype, n_rows,

@@ -70,6 +70,8 @@ SIGNATURES = {
     "cab_index_launch_count": (_i64, [_p]),
     "cab_index_last_scan_ms": (_dbl, [_p]),
     "cab_score_all": (_i32, [_p, _p, _i32, _i32, _p, _p, _i32, _p]),
+    "cab_index_write_flags": (_i32, [_p, _i64, _i64, _p, _i32]),
+    "cab_index_read_flags": (_i32, [_p, _i64, _i64, _p, _i32]),
 }
 
 _lib = None

@@ -420,6 +420,30 @@ int cab_index_read_rows(cab_index *idx, int corpus, int64_t r0, int64_t r1, floa
     return CAB_OK;
 }
 
+int cab_index_write_flags(cab_index *idx, int64_t r0, int64_t r1, const uint8_t *flags, int flags_loc) {
+    CHECK_HANDLE(idx);
+    if (!flags || r0 < 0 || r1 < r0 || r1 > idx->size) return fail(idx, CAB_ERR_INVALID, "bad flag range");
+    if (flags_loc != CAB_HOST && flags_loc != CAB_DEVICE) return fail(idx, CAB_ERR_INVALID, "flags_loc");
+    if (r1 == r0) return CAB_OK;
+    CU(idx, cudaSetDevice(idx->device));
+    CU(idx, cudaMemcpyAsync(idx->flags + r0, flags, size_t(r1 - r0),
+                            flags_loc == CAB_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, idx->own_stream));
+    CU(idx, cudaStreamSynchronize(idx->own_stream));
+    return CAB_OK;
+}
+
+int cab_index_read_flags(cab_index *idx, int64_t r0, int64_t r1, uint8_t *out, int out_loc) {
+    CHECK_HANDLE(idx);
+    if (!out || r0 < 0 || r1 < r0 || r1 > idx->size) return fail(idx, CAB_ERR_INVALID, "bad flag range");
+    if (out_loc != CAB_HOST && out_loc != CAB_DEVICE) return fail(idx, CAB_ERR_INVALID, "out_loc");
+    if (r1 == r0) return CAB_OK;
+    CU(idx, cudaSetDevice(idx->device));
+    CU(idx, cudaMemcpyAsync(out, idx->flags + r0, size_t(r1 - r0),
+                            out_loc == CAB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, idx->own_stream));
+    CU(idx, cudaStreamSynchronize(idx->own_stream));
+    return CAB_OK;
+}
+
 // ---- persistent index file ---------------------------------------------------------------------
 namespace {
 struct FileHeader {

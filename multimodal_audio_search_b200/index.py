@@ -178,6 +178,35 @@ class SegmentIndex:
         N.check(self._lib.cab_index_read_rows(self._h, corpus, r0, r1, _ptr(out), N.CAB_HOST), self._h)
         return out
 
+    def read_flags(self, r0: int = 0, r1: "int | None" = None) -> np.ndarray:
+        """Flag bytes of rows [r0, r1): bit0 asr_success, bit1 audio_success, bits 2-3 weight class."""
+        r1 = len(self) if r1 is None else r1
+        out = np.empty(max(r1 - r0, 0), dtype=np.uint8)
+        N.check(self._lib.cab_index_read_flags(self._h, int(r0), int(r1), _ptr(out), N.CAB_HOST), self._h)
+        return out
+
+    def write_flags(self, flags, r0: int = 0):
+        """Overwrite the flag bytes of rows [r0, r0 + len(flags)) (numpy uint8 or CUDA uint8 tensor)."""
+        if _is_torch_cuda(flags):
+            import torch
+            if flags.dtype != torch.uint8 or flags.dim() != 1 or not flags.is_contiguous():
+                raise ValueError("flags must be a contiguous uint8 vector")
+            torch.cuda.current_stream(self.device).synchronize()      # the copy runs on the handle's own stream
+            N.check(self._lib.cab_index_write_flags(self._h, int(r0), int(r0) + flags.numel(),
+                                                    C.c_void_p(flags.data_ptr()), N.CAB_DEVICE), self._h)
+            return
+        f = np.ascontiguousarray(flags, dtype=np.uint8).reshape(-1)
+        N.check(self._lib.cab_index_write_flags(self._h, int(r0), int(r0) + f.size, _ptr(f), N.CAB_HOST), self._h)
+
+    def set_weight_classes(self, classes, r0: int = 0):
+        """Assign the 2-bit weight class (0..3) of rows [r0, r0 + len(classes)) for `score_all`,
+        keeping their success bits."""
+        c = np.ascontiguousarray(classes).reshape(-1)
+        if c.size and (c.min() < 0 or c.max() > 3):
+            raise ValueError("weight classes must be in 0..3")
+        cur = self.read_flags(r0, r0 + c.size)
+        self.write_flags((cur & 3) | (c.astype(np.uint8) << 2), r0)
+
     # -- search --------------------------------------------------------------------------------
     @staticmethod
     def _weights(w_asr, w_audio, nq):

@@ -82,3 +82,44 @@ def test_10m_bf16_batch256_top100_tensor_cores():
     hits = sum(len(set(gm.indices[i].tolist()) & set(gv.indices[i].tolist())) for i in range(32))
     assert hits / (32 * k) >= 0.99                                   # differences only at the k-th boundary
     idx.close()
+
+
+def test_10m_legacy_scores_are_bit_exact_combinations():
+    """cab_score_all at BASELINE size (10 M segments, bf16 rows): size-independent properties.
+    asr_only / caption_only return the two cosines themselves, so every weighted mode must be
+    BIT-identical to numpy's float32 `w_a * s_asr + w_b * s_caption` of those two vectors with the
+    row's class weights (previous_iterations/streamlit_app.py:217/:219); planted rows carry the
+    oracle's score; the top-k search agrees with the score vector where both rules coincide."""
+    n_queries = 2
+    idx = SegmentIndex("bf16", capacity=N_ROWS)
+    idx.append_synth(SEED, N_ROWS, 0, N_ROWS, n_queries=n_queries, plants=PLANTS, partial=False)
+    cls = no.legacy_good_speech(SEED, N_ROWS).astype(np.uint8) * 1 + (np.arange(N_ROWS) % 7 == 0).astype(np.uint8) * 2
+    idx.set_weight_classes(cls)
+    flags = idx.read_flags()
+    assert np.array_equal(flags >> 2, cls) and np.all((flags & 3) == 3)
+    q = synth.raw_queries(SEED, 0, n_queries)
+    s_asr = idx.score_all(q, no.LEGACY_CLASS_WEIGHTS["asr_only"])
+    s_cap = idx.score_all(q, no.LEGACY_CLASS_WEIGHTS["caption_only"])
+    assert s_asr.shape == (n_queries, N_ROWS) and np.isfinite(s_asr).all() and np.abs(s_asr).max() <= 1.0 + 1e-3
+    table = np.array([[0.2, 0.8], [0.7, 0.3], [-0.5, 1.5], [0.25, 0.0]], dtype=np.float32)
+    got = idx.score_all(q, table)
+    for qi in range(n_queries):
+        want = table[cls, 0] * s_asr[qi] + table[cls, 1] * s_cap[qi]          # float32, op by op
+        assert want.dtype == np.float32
+        assert np.array_equal(got[qi], want)
+        truth = _planted_truth(qi, q[qi], 0.5, 0.5, n_queries)                  # oracle cosines of the planted rows
+        for r, (_, sa, sb) in truth.items():
+            assert abs(s_asr[qi, r] - sa) <= BF16_TOL and abs(s_cap[qi, r] - sb) <= BF16_TOL
+        # idempotence
+        assert np.array_equal(idx.score_all(q[qi], table)[0], got[qi])
+    # both pipelines successful + weights summing to 1: the current engine's fusion is the same
+    # linear form, so its top-10 must be the 10 largest entries of the score vector
+    half = idx.score_all(q, [[0.5, 0.5]] * 4)
+    res = idx.search(q, 0.5, 0.5, k=10, threshold=0.1, path="gemv")
+    for qi in range(n_queries):
+        gi, gf = _check_properties(res, qi)
+        top = np.argpartition(-half[qi], 10)[:10]
+        kth = np.sort(half[qi][top])[0]
+        assert np.abs(half[qi][gi] - gf).max() <= 1e-6
+        assert all(half[qi][i] >= kth - 1e-6 for i in gi)
+    idx.close()

@@ -32,5 +32,25 @@ for dtype, nq, k, path in (("fp32", 1, 10, "gemv"), ("fp32", 3, 10, "gemv"), ("b
         assert same >= (1.0 if path == "gemv" else 0.6), same      # gemm: per-shard bf16-query selection may differ at the k-th boundary
         print(f"{dtype} Q={nq} k={k} {path}: p2p == nccl on all ranks; identical to the unsharded index for {same*100:.0f}% of queries", flush=True)
     dist.barrier()
+# legacy all-N scoring over the shards: one all-gather of the score vectors, every rank gets [Q, n]
+for dtype in ("fp32", "bf16"):
+    lo, hi = shard_range(n, rank, world)
+    idx = SegmentIndex(dtype, capacity=hi - lo, device=local)
+    idx.append_synth(seed, n, lo, hi, n_queries=2, plants=40, partial=True)
+    idx.row_base = lo
+    cls = (np.arange(lo, hi) % 3).astype(np.uint8)
+    idx.set_weight_classes(cls)
+    q = torch.from_numpy(synth.raw_queries(seed, 0, 2)).cuda()
+    table = [[0.2, 0.8], [0.7, 0.3], [1.0, 0.0], [0.0, 1.0]]
+    full = ShardedSearcher(idx, rank, world).score_all(q, table, n)
+    assert full.shape == (2, n) and full.is_cuda
+    if rank == 0:
+        whole = SegmentIndex(dtype, capacity=n, device=local)
+        whole.append_synth(seed, n, 0, n, n_queries=2, plants=40, partial=True)
+        whole.set_weight_classes((np.arange(n) % 3).astype(np.uint8))
+        ref = whole.score_all(q, table)
+        assert torch.equal(full, ref), dtype
+        print(f"{dtype}: sharded score_all == unsharded, bit for bit ({world} ranks, {n} segments)", flush=True)
+    dist.barrier()
 if rank == 0: print("p2p check ok")
 dist.destroy_process_group()
