@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cfloat>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -642,6 +643,14 @@ static int make_emit(cab_index *idx, int n_lists, int nq, int k, double threshol
     return CAB_OK;
 }
 
+// fp32 scan weight w / (w_asr + w_audio).  The scan tells "this pipeline's query weight is 0"
+// (rows that only have this pipeline are skipped, :659-661) from "positive" by the sign of the
+// staged value, so a positive weight never rounds to 0.
+static float stage_weight(double w, double tot) {
+    if (!(w > 0) || !(tot > 0)) return 0.f;
+    return std::max(float(w / tot), FLT_MIN);
+}
+
 // One H2D copy of the per-search parameter block (weights, and the queries if they are on the host).
 static int stage_params(cab_index *idx, const float *queries, int queries_loc, const double *w_asr,
                         const double *w_audio, int nq, cudaStream_t s, const float **dq) {
@@ -655,8 +664,8 @@ static int stage_params(cab_index *idx, const float *queries, int queries_loc, c
     for (int i = 0; i < nq; ++i) {
         h64[i] = w_asr[i]; h64[nq + i] = w_audio[i];
         const double tot = w_asr[i] + w_audio[i];
-        h32[i] = tot > 0 ? float(w_asr[i] / tot) : 0.f;
-        h32[nq + i] = tot > 0 ? float(w_audio[i] / tot) : 0.f;
+        h32[i] = stage_weight(w_asr[i], tot);
+        h32[nq + i] = stage_weight(w_audio[i], tot);
     }
     if (qbytes) memcpy(idx->h_in + wbytes, queries, qbytes);
     CU(idx, cudaMemcpyAsync(idx->d_params, idx->h_in, wbytes + qbytes, cudaMemcpyHostToDevice, s));
@@ -688,6 +697,8 @@ static int run_local(cab_index *idx, const float *queries, int queries_loc, cons
     for (int i = 0; i < nq; ++i)
         if (!(std::isfinite(w_asr[i]) && std::isfinite(w_audio[i]) && w_asr[i] >= 0 && w_audio[i] >= 0))
             return fail(idx, CAB_ERR_INVALID, "weights must be finite and >= 0");
+    for (int i = 0; i < nq; ++i)
+        if (!(w_asr[i] + w_audio[i] > 0)) return fail(idx, CAB_ERR_INVALID, "w_asr + w_audio must be > 0 for every query");
     bool use_gemm = false;
     if (path == CAB_PATH_GEMM) {
         if (idx->dtype != CAB_BF16) return fail(idx, CAB_ERR_INVALID, "the tensor-core path needs a bf16 index");
@@ -708,8 +719,8 @@ static int run_local(cab_index *idx, const float *queries, int queries_loc, cons
     if (nq == 1 && !use_gemm) {
         const double tot = w_asr[0] + w_audio[0];
         inl.use_weights = 1;
-        inl.wa32 = tot > 0 ? float(w_asr[0] / tot) : 0.f;
-        inl.wb32 = tot > 0 ? float(w_audio[0] / tot) : 0.f;
+        inl.wa32 = stage_weight(w_asr[0], tot);
+        inl.wb32 = stage_weight(w_audio[0], tot);
         inl.w64_asr = w_asr[0]; inl.w64_audio = w_audio[0];
         if (queries_loc == CAB_HOST) { inl.use_query = 1; memcpy(inl.q, queries, sizeof inl.q); dq = reinterpret_cast<const float *>(idx->d_params); }
         else dq = queries;

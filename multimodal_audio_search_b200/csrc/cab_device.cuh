@@ -55,12 +55,14 @@ struct ScanWeights {
     float wa, wb;          // w_asr/(w_asr+w_audio), w_audio/(w_asr+w_audio) as fp32
 };
 __device__ __forceinline__ float fuse32(float sa, float sb, uint32_t flags, ScanWeights w) {
-    // both pipelines: (wa, wb); one: weight 1 on it; none: the row is skipped (-inf).
-    float ea = (flags & 1u) ? ((flags & 2u) ? w.wa : 1.0f) : 0.0f;
-    float eb = (flags & 2u) ? ((flags & 1u) ? w.wb : 1.0f) : 0.0f;
+    // both pipelines: (wa, wb); one: weight 1 on it -- unless its query weight is 0, then the
+    // effective weights sum to 0 and the row is skipped (:659-661); none: skipped (-inf).
+    // (a positive query weight is staged as a positive fp32, see stage_weight in cab_api.cu)
+    float ea = (flags & 1u) ? ((flags & 2u) ? w.wa : (w.wa > 0.f ? 1.0f : 0.0f)) : 0.0f;
+    float eb = (flags & 2u) ? ((flags & 1u) ? w.wb : (w.wb > 0.f ? 1.0f : 0.0f)) : 0.0f;
     float f = fmaf(ea, sa, eb * sb);
     // :654 gate (redundant for the reference's positive threshold, kept for any threshold)
-    return ((flags & 3u) && (sa > 0.f || sb > 0.f)) ? f : -INFINITY;
+    return ((ea > 0.f || eb > 0.f) && (sa > 0.f || sb > 0.f)) ? f : -INFINITY;
 }
 
 // ---- bitonic sort (descending) of a power-of-two array of u64 keys in shared memory, by one

@@ -16,6 +16,14 @@ characters) and one `cab_score_all` launch produces the N scores on the GPU.
 * `accelerate_legacy(system)` patches a reference `UnifiedAudioSearch` object in place;
 * `UnifiedAudioSearch` is a standalone mirror of its search-side surface (`sentence_model`,
   `search(query_text, audio_database, strategy)`).
+
+The other earlier engine, `previous_iterations/clean_audio_search.py`, searches ONE stored embedding
+per segment (`search_audio(query, search_mode)`, :293-320: "combined" / "asr" / "caption", raw dot
+product, strict `> 0.1`, stable sort, top 10).  `accelerate_clean(system)` / `CleanAudioSearch`
+serve it with the top-k scan: a single-corpus search is the fused search with weights (1, 0) or
+(0, 1) (rows lacking that embedding are skipped, audio_search.py:659-661 rule), on unit-length
+embeddings the raw dot product is the cosine, and the few winners are re-scored on the host with
+the reference's own expression so the returned similarities are the reference's floats.
 """
 from __future__ import annotations
 
@@ -122,3 +130,104 @@ class UnifiedAudioSearch:
     def top_indices(similarities: np.ndarray, top_k: int) -> np.ndarray:
         """What the reference UI does with the vector (:410)."""
         return np.argsort(similarities)[::-1][:top_k]
+
+
+# ---- clean_audio_search.py: search_audio(query, search_mode) ------------------------------------------
+CLEAN_TOP_K = 10            # clean_audio_search.py:320
+CLEAN_THRESHOLD = 0.1       # :312
+_CLEAN_OVERFETCH = 64       # candidates taken from the GPU before the exact host re-score
+_NORM_TOL = 1e-3
+_CLEAN_KEYS = {"combined": "combined_embedding", "asr": "asr_embedding", "caption": "caption_embedding"}
+
+
+def _unit_row(e, what: str) -> np.ndarray:
+    a = _row(e)
+    norm = float(np.linalg.norm(a.astype(np.float64)))
+    if abs(norm - 1.0) > _NORM_TOL:
+        raise ValueError(f"{what} has length {norm:.4f}: ranking by raw dot product (clean_audio_search.py:306) "
+                         "is served by the cosine scan only for unit-length embeddings (all-MiniLM-L6-v2 produces them)")
+    return a
+
+
+class _CleanDatabase:
+    """Two indexes in step with the append-only `audio_database` (:115-187): (asr, caption) rows
+    in one, the combined embedding in the other (its second corpus stays empty)."""
+
+    def __init__(self, dtype: str = "fp32", device: int = 0):
+        self.dtype, self.device = dtype, device
+        self.pair: SegmentIndex | None = None
+        self.combined: SegmentIndex | None = None
+        self.n_synced = 0
+        self._list = None
+        self._last = None
+
+    def sync(self, database: List[Dict]):
+        if self.pair is None:
+            cap = max(1024, len(database))
+            self.pair = SegmentIndex(self.dtype, capacity=cap, device=self.device)
+            self.combined = SegmentIndex(self.dtype, capacity=cap, device=self.device)
+        replaced = database is not self._list or self.n_synced > len(database) or \
+            (self.n_synced and database[self.n_synced - 1] is not self._last)
+        if replaced:
+            self.pair.clear()
+            self.combined.clear()
+            self.n_synced = 0
+            self._list = database
+        n_new = len(database) - self.n_synced
+        if n_new > 0:
+            rows = {key: np.zeros((n_new, DIM), dtype=np.float32) for key in _CLEAN_KEYS.values()}
+            has = {key: np.zeros(n_new, dtype=np.uint8) for key in _CLEAN_KEYS.values()}
+            for i, seg in enumerate(database[self.n_synced:]):
+                for key in _CLEAN_KEYS.values():
+                    if seg.get(key) is not None:
+                        rows[key][i] = _unit_row(seg[key], f"segment {self.n_synced + i} {key}")
+                        has[key][i] = 1
+            self.pair.append(rows["asr_embedding"], rows["caption_embedding"],
+                             has["asr_embedding"] | (has["caption_embedding"] << 1))
+            self.combined.append(rows["combined_embedding"], None, has["combined_embedding"])
+            self.n_synced = len(database)
+            self._last = database[-1]
+        return self.pair, self.combined
+
+
+def _b200_search_audio(self, query: str, search_mode: str = "combined") -> List[Dict]:
+    """GPU-backed body of clean_audio_search.py `search_audio`."""
+    if not self.audio_database:                                               # :295-296
+        return []
+    query_embedding = self.text_embedder.encode(query)                        # :299
+    key = _CLEAN_KEYS.get(search_mode)
+    if key is None:
+        return []                                                             # every similarity stays 0.0 (:303-310)
+    q = _unit_row(query_embedding, "the query embedding")
+    pair, combined = self._cab_database.sync(self.audio_database)
+    index, wa, wb = (combined, 1.0, 0.0) if search_mode == "combined" else \
+        (pair, 1.0, 0.0) if search_mode == "asr" else (pair, 0.0, 1.0)
+    res = index.search(q[None, :], wa, wb, k=_CLEAN_OVERFETCH, threshold=CLEAN_THRESHOLD - 10 * _NORM_TOL)
+    scored = []
+    for j in range(int(res.count[0])):
+        i = int(res.indices[0, j])
+        segment = self.audio_database[i]
+        similarity = float(np.dot(query_embedding, segment[key]))             # :306-310, the reference's own float
+        if similarity > CLEAN_THRESHOLD:                                      # :312
+            scored.append((-similarity, i, segment, similarity))
+    scored.sort(key=lambda t: (t[0], t[1]))                                   # :319 stable descending
+    return [{**segment, "similarity": similarity} for _, _, segment, similarity in scored[:CLEAN_TOP_K]]   # :313-320
+
+
+def accelerate_clean(system, dtype: str = "fp32", device: int = 0):
+    """Replace `system.search_audio` (a clean_audio_search.py `UnifiedAudioSearch`, or any object
+    with `text_embedder` and `audio_database`) by the B200 path.  Returns the same object."""
+    system._cab_database = _CleanDatabase(dtype, device)
+    system.search_audio = types.MethodType(_b200_search_audio, system)
+    return system
+
+
+class CleanAudioSearch:
+    """Search-side mirror of clean_audio_search.py's `UnifiedAudioSearch` (:26-68, :293-320)."""
+
+    def __init__(self, dtype: str = "fp32", device: int = 0, text_embedder=None):
+        self.text_embedder = text_embedder
+        self.audio_database: List[Dict] = []                                  # :66
+        self._cab_database = _CleanDatabase(dtype, device)
+
+    search_audio = _b200_search_audio

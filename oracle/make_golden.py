@@ -16,6 +16,8 @@ Fixtures (all outputs come from the reference's own `search_with_fusion` /
                       vectors incl. None / zero / scaled rows) + the reference's answers.
   flag_cases.json     libraries where `*_success` and "embedding present" disagree.
   query_weights.json  query strings -> (asr_weight, audio_weight, analysis).
+  clean_search.json   `previous_iterations/clean_audio_search.py:293-320` (`search_audio`): top-10
+                      segment ids and similarities for the modes asr / caption / combined.
   legacy_scores.npz   the earlier engine (`previous_iterations/streamlit_app.py:173-223`,
                       `UnifiedAudioSearch.search`): all-N similarity vectors for the strategies
                       asr_only / caption_only / adaptive on seeded libraries.
@@ -249,6 +251,27 @@ def legacy_scores():
     print("legacy", len(out))
 
 
+CLEAN_CASES = [("clean_700", 55, 700, 14), ("clean_90", 56, 90, 4)]
+
+
+def clean_cases():
+    out = []
+    for name, seed, n, plants in CLEAN_CASES:
+        a, c, m, ha, hc, q, qm = no.clean_library(seed, n, 2, plants)
+        db = rs.clean_database(a, c, m, ha, hc)
+        rec = {"name": name, "seed": seed, "n_rows": n, "plants": plants, "queries": []}
+        for qi in range(2):
+            for mode, qv in (("asr", q[qi]), ("caption", q[qi]), ("combined", qm[qi]), ("no_such_mode", q[qi])):
+                res = rs.clean_search(f"q{qi}", qv, db, mode)
+                rec["queries"].append({"qi": qi, "mode": mode,
+                                       "indices": [int(r["segment_id"][4:]) for r in res],
+                                       "similarity": [r["similarity"] for r in res]})
+        out.append(rec)
+    with open(os.path.join(GOLD, "clean_search.json"), "w") as fjs:
+        json.dump(out, fjs, indent=1)
+    print("clean", sum(len(r["queries"]) for r in out))
+
+
 if __name__ == "__main__":
     if not rs.available():
         sys.exit("reference not present: goldens can only be minted in the build container")
@@ -259,3 +282,5 @@ if __name__ == "__main__":
     search_cases()
     if rs.legacy_available():
         legacy_scores()
+    if rs.clean_available():
+        clean_cases()

@@ -203,3 +203,35 @@ def class_weight_scores(q, asr_rows, caption_rows, has_asr, has_caption, row_cla
     table = np.asarray(class_weights, dtype=np.float32).reshape(4, 2)
     cls = np.asarray(row_class, dtype=np.int64) & 3
     return (table[cls, 0] * sa + table[cls, 1] * sb).astype(np.float32)
+
+
+# ---- clean_audio_search.py `search_audio` (:293-320) ----------------------------------------------
+def clean_library(seed: int, n: int, n_queries: int, plants: int):
+    """Unit-length synthetic embeddings for the clean_audio_search.py tests: (asr, caption, combined,
+    has_asr, has_caption, queries), all float32, regenerated from the seed."""
+    from multimodal_audio_search_b200 import synth
+    a, c, f, _ = synth.library(seed, n, n_queries, plants, True)
+    m, _, _, _ = synth.library(seed + 1000, n, n_queries, plants, False)
+    q = synth.raw_queries(seed, 0, n_queries)
+    qm = synth.raw_queries(seed + 1000, 0, n_queries)
+
+    def unit(x):
+        x = np.asarray(x, dtype=np.float32)
+        nrm = np.sqrt(np.einsum("ij,ij->i", x, x))
+        nrm[nrm == 0] = 1
+        return (x / nrm[:, None]).astype(np.float32)
+    # the combined corpus is planted for the second library's queries: blend both query sets so
+    # every mode has neighbours for query i
+    return unit(a), unit(c), unit(m), (f & 1).astype(bool), (f & 2).astype(bool), unit(q), unit(qm)
+
+
+def clean_search(q, rows, has, k: int = 10, threshold: float = 0.1):
+    """Raw dot product (no normalisation, :306-310) of the query with one stored embedding per
+    segment, 0.0 where it is missing, strict `> 0.1` (:312), stable descending sort (:319), top 10
+    (:320).  Returns (indices, similarities as Python-float-valued float64)."""
+    q = np.asarray(q, dtype=np.float32)
+    rows = np.asarray(rows, dtype=np.float32)
+    sims = np.array([float(np.dot(q, rows[i])) if has[i] else 0.0 for i in range(len(rows))], dtype=np.float64)
+    passing = np.nonzero(sims > threshold)[0]
+    order = passing[np.argsort(-sims[passing], kind="stable")][:k]
+    return order.astype(np.int64), sims[order]

@@ -113,6 +113,55 @@ def legacy_search(query_text: str, query_vec, database, strategy: str) -> np.nda
     return eng.search(query_text, database, strategy)
 
 
+CLEAN_FILE = os.path.join(os.path.dirname(REFERENCE_FILE), "previous_iterations", "clean_audio_search.py")
+_clean = None
+
+
+def clean_available() -> bool:
+    return os.path.exists(CLEAN_FILE)
+
+
+def load_clean():
+    """Import previous_iterations/clean_audio_search.py for its `search_audio` (:293-320)."""
+    global _clean
+    if _clean is not None:
+        return _clean
+    if not clean_available():
+        raise FileNotFoundError(CLEAN_FILE)
+    load()                                          # installs the stub modules
+    spec = importlib.util.spec_from_file_location("reference_clean_app", CLEAN_FILE)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    _clean = mod
+    return mod
+
+
+def clean_database(asr, caption, combined, has_asr, has_caption) -> list[dict]:
+    """Segments as clean_audio_search.py stores them (:175-187); a segment always has a combined
+    embedding (it is only stored when some text exists, :171)."""
+    db = []
+    for i in range(len(has_asr)):
+        db.append({
+            "segment_id": f"seg_{i}", "start_time": 10.0 * i, "end_time": 10.0 * i + 10.0,
+            "asr_text": f"words {i}" if has_asr[i] else "", "caption_text": f"sound {i}" if has_caption[i] else "",
+            "combined_text": f"words sound {i}",
+            "asr_embedding": np.asarray(asr[i], dtype=np.float32) if has_asr[i] else None,
+            "caption_embedding": np.asarray(caption[i], dtype=np.float32) if has_caption[i] else None,
+            "combined_embedding": np.asarray(combined[i], dtype=np.float32),
+            "audio_data": None, "sample_rate": 16000,
+        })
+    return db
+
+
+def clean_search(query_text: str, query_vec, database, search_mode: str):
+    """Run the reference's own `UnifiedAudioSearch.search_audio` (clean_audio_search.py)."""
+    mod = load_clean()
+    eng = mod.UnifiedAudioSearch.__new__(mod.UnifiedAudioSearch)
+    eng.text_embedder = FakeEmbedder({query_text: query_vec})
+    eng.audio_database = database
+    return eng.search_audio(query_text, search_mode)
+
+
 class FakeEmbedder:
     """Stands in for SentenceTransformer: `.encode(text)` returns the vector registered for it."""
 

@@ -154,3 +154,53 @@ def test_drop_in_for_the_earlier_engine():
     patched = legacy.accelerate_legacy(ReferenceLike())
     sims = patched.search("query 1", db, "caption_only")
     assert np.abs(sims - z[f"{m['name']}/1/caption_only"]).max() <= 1e-5
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_drop_in_for_clean_audio_search(dtype):
+    """`search_audio(query, search_mode)` of previous_iterations/clean_audio_search.py:293-320 on
+    the GPU: same segment ids, and -- re-scored on the host with the reference's expression -- the
+    same similarity floats as the oracle computes here (golden values within 1e-6)."""
+    from oracle.reference_shim import FakeEmbedder, clean_database
+    cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "clean_search.json")))
+    for case in cases:
+        a, c, m, ha, hc, q, qm = no.clean_library(case["seed"], case["n_rows"], 2, case["plants"])
+        db = clean_database(a, c, m, ha, hc)
+        texts = {}
+        for rec in case["queries"]:
+            texts[f"{rec['mode']} {rec['qi']}"] = (qm if rec["mode"] == "combined" else q)[rec["qi"]]
+        eng = legacy.CleanAudioSearch(dtype=dtype, text_embedder=FakeEmbedder(texts))
+        assert eng.search_audio("asr 0", "asr") == []                             # empty database (:295)
+        half = len(db) // 2
+        eng.audio_database.extend(db[:half])
+        eng.search_audio("asr 0", "asr")
+        eng.audio_database.extend(db[half:])                                      # grows like the app's list
+        everything = np.ones(case["n_rows"], bool)
+        for rec in case["queries"]:
+            got = eng.search_audio(f"{rec['mode']} {rec['qi']}", rec["mode"])
+            assert [int(r["segment_id"][4:]) for r in got] == rec["indices"]
+            np.testing.assert_allclose([r["similarity"] for r in got], rec["similarity"], atol=1e-6, rtol=0)
+            if rec["mode"] in ("asr", "caption", "combined"):
+                rows, has, qv = {"asr": (a, ha, q), "caption": (c, hc, q), "combined": (m, everything, qm)}[rec["mode"]]
+                _, sims = no.clean_search(qv[rec["qi"]], rows, has)
+                assert [r["similarity"] for r in got] == sims.tolist()            # the reference's own floats
+            for r in got:
+                assert set(r) == set(db[0]) | {"similarity"} and type(r["similarity"]) is float
+    # non-unit embeddings: raw-dot ranking is not the cosine ranking -> refused, not approximated
+    bad = legacy.CleanAudioSearch(text_embedder=FakeEmbedder({"x": q[0]}))
+    seg = dict(db[0]); seg["combined_embedding"] = 2.0 * seg["combined_embedding"]
+    bad.audio_database.append(seg)
+    with pytest.raises(ValueError, match="unit-length"):
+        bad.search_audio("x", "combined")
+
+    class ReferenceLike:
+        def __init__(self):
+            self.text_embedder = FakeEmbedder({"x": q[0]})
+            self.audio_database = db
+
+        def search_audio(self, *a, **k):
+            raise AssertionError("CPU path must not run")
+    patched = legacy.accelerate_clean(ReferenceLike(), dtype=dtype)
+    idx, sims = no.clean_search(q[0], a, ha)
+    got = patched.search_audio("x", "asr")
+    assert [int(r["segment_id"][4:]) for r in got] == idx.tolist() and [r["similarity"] for r in got] == sims.tolist()

@@ -310,6 +310,36 @@ def test_config2_one_million_fp32():
     np.testing.assert_allclose(np.sort(bf)[::-1], of, atol=BF16_TOL, rtol=0)
 
 
+@pytest.mark.parametrize("dtype,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+def test_zero_query_weight_skips_rows_that_only_have_that_pipeline(dtype, tol):
+    """Weights (1, 0) / (0, 1) -- single-corpus search, as in the earlier engines.  A row whose only
+    successful pipeline carries weight 0 has effective weights summing to 0 and is skipped
+    (audio_search.py:659-661); it must not crowd real results out of the scan's top-k either."""
+    seed, n = 77, 20000
+    a, b, f, _ = synth.library(seed, n, 2, 30, True)
+    q = synth.raw_queries(seed, 0, 2)
+    # make the single-pipeline rows the best matches of the corpus that will carry weight 0
+    only_audio = np.nonzero(f == 2)[0][:200]
+    only_asr = np.nonzero(f == 1)[0][:200]
+    b[only_audio] = q[0] + 0.05 * b[only_audio]
+    a[only_asr] = q[0] + 0.05 * a[only_asr]
+    idx = _index_from(a, b, f, dtype)
+    for wa, wb in ((1.0, 0.0), (0.0, 1.0), (1e-300, 1.0)):
+        for k in (10, 100):
+            res = idx.search(q, wa, wb, k=k)
+            for qi in range(2):
+                o = no.search(q[qi], a, b, f, wa, wb, k=k)
+                gi, gf, _, _, gfl = result_row(res, qi)
+                assert_topk_matches(gi, gf, o, tol, k=k)
+                if wb == 0.0:
+                    assert not np.isin(gi, only_audio).any() and (gfl & 1).all()
+                if wa == 0.0:
+                    assert not np.isin(gi, only_asr).any() and (gfl & 2).all()
+    with pytest.raises(Exception, match="must be > 0"):
+        idx.search(q, 0.0, 0.0)
+    idx.close()
+
+
 def test_invalid_arguments_are_rejected_not_computed():
     import ctypes as C
     from multimodal_audio_search_b200 import _native as N

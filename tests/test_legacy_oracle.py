@@ -87,3 +87,38 @@ def test_oracle_matches_the_reference_live():
         assert ref.shape == (n,)
         assert np.abs(ref - got.astype(np.float64)).max() <= TOL
     assert rs.legacy_search("a query", q, [], "adaptive").shape == (0,)
+
+
+# ---- previous_iterations/clean_audio_search.py: search_audio (:293-320) ----------------------------
+CLEAN_GOLD = os.path.join(os.path.dirname(__file__), "golden", "clean_search.json")
+_MODE_ROWS = {"asr": 0, "caption": 1, "combined": 2}
+
+
+def test_clean_search_oracle_matches_golden_vectors():
+    cases = json.load(open(CLEAN_GOLD))
+    assert len(cases) >= 2
+    for case in cases:
+        a, c, m, ha, hc, q, qm = no.clean_library(case["seed"], case["n_rows"], 2, case["plants"])
+        everything = np.ones(case["n_rows"], bool)
+        for rec in case["queries"]:
+            if rec["mode"] not in _MODE_ROWS:
+                assert rec["indices"] == []                       # unknown mode: every similarity 0.0
+                continue
+            rows, has, qv = {"asr": (a, ha, q), "caption": (c, hc, q), "combined": (m, everything, qm)}[rec["mode"]]
+            idx, sims = no.clean_search(qv[rec["qi"]], rows, has)
+            assert idx.tolist() == rec["indices"]
+            np.testing.assert_allclose(sims, rec["similarity"], atol=1e-6, rtol=0)
+            assert len(idx) <= 10 and (sims > 0.1).all() and all(sims[j] >= sims[j + 1] for j in range(len(sims) - 1))
+
+
+@pytest.mark.skipif(not rs.clean_available(), reason="reference not mounted (GPU box)")
+def test_clean_search_oracle_matches_the_reference_live():
+    a, c, m, ha, hc, q, qm = no.clean_library(91, 300, 2, 9)
+    db = rs.clean_database(a, c, m, ha, hc)
+    for mode, rows, has, qv in (("asr", a, ha, q[0]), ("caption", c, hc, q[1]), ("combined", m, np.ones(300, bool), qm[0])):
+        ref = rs.clean_search("text", qv, db, mode)
+        idx, sims = no.clean_search(qv, rows, has)
+        assert [int(r["segment_id"][4:]) for r in ref] == idx.tolist()
+        assert [r["similarity"] for r in ref] == sims.tolist()     # same expression, same floats
+        assert all(set(r) == set(db[0]) | {"similarity"} for r in ref)
+    assert rs.clean_search("text", q[0], [], "asr") == []
