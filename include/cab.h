@@ -137,6 +137,9 @@ CAB_API int cab_index_file_info(const char *path, int *dim, int *dtype, int64_t 
  * queries : fp32 [n_queries x dim], raw (re-normalised like normalize(X) at :646);
  * w_asr, w_audio : host arrays [n_queries] of the query weights from
  *                  _analyze_query_for_weights (:632), float64 like the reference's floats;
+ *                  finite, >= 0, w_asr + w_audio > 0.  A weight of 0 makes the search
+ *                  single-corpus: rows whose only successful pipeline carries weight 0 have
+ *                  effective weights summing to 0 and are skipped (:659-661);
  * k <= CAB_MAX_K; threshold: the reference's 0.1 (:672), strict `>` evaluated in float64.
  * Outputs (each [n_queries x k], may be NULL if not wanted; host or device per out_loc):
  *   out_index  global segment index, best first (score desc, index asc = Python's stable
