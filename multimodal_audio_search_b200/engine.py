@@ -136,21 +136,13 @@ class _DeviceLibrary:
         return self.index
 
 
-def _b200_search_with_fusion(self, query: str) -> Tuple[List[Dict], Dict]:
-    """GPU-backed body of search_with_fusion; `self` is a reference-compatible engine."""
-    if not self.audio_segments:                                       # :626-627
-        return [], {}
-    start_time = time.time()
-    asr_weight, audio_weight, weight_analysis = self._analyze_query_for_weights(query)   # :632
-    query_embedding = _embedding_row(self.text_embedder.encode(query))                   # :635
-    index = self._cab_library.sync(self.audio_segments)
-    res = index.search(query_embedding[None, :], asr_weight, audio_weight, k=TOP_K, threshold=THRESHOLD)
-
+def _materialise(self, res, qi: int, asr_weight: float, audio_weight: float) -> List[Dict]:
+    """Result dicts of query row `qi` of a SearchResult, as the reference builds them (:653-682)."""
     results = []
-    for j in range(int(res.count[0])):
-        segment = self.audio_segments[int(res.indices[0, j])]
-        asr_similarity = float(res.asr_sim[0, j])                     # :646
-        audio_similarity = float(res.audio_sim[0, j])                 # :651
+    for j in range(int(res.count[qi])):
+        segment = self.audio_segments[int(res.indices[qi, j])]
+        asr_similarity = float(res.asr_sim[qi, j])                    # :646
+        audio_similarity = float(res.audio_sim[qi, j])                # :651
         effective_asr_weight = asr_weight if segment["asr_success"] else 0       # :656-657
         effective_audio_weight = audio_weight if segment["audio_success"] else 0
         total_weight = effective_asr_weight + effective_audio_weight
@@ -170,11 +162,54 @@ def _b200_search_with_fusion(self, query: str) -> Tuple[List[Dict], Dict]:
         # :673-682; a columnar record keeps audio_data / embeddings lazy until the UI reads them
         results.append(segment.with_fields(**scores) if isinstance(segment, SegmentRecord)
                        else {**segment, **scores})
+    return results
+
+
+def _b200_search_with_fusion(self, query: str) -> Tuple[List[Dict], Dict]:
+    """GPU-backed body of search_with_fusion; `self` is a reference-compatible engine."""
+    if not self.audio_segments:                                       # :626-627
+        return [], {}
+    start_time = time.time()
+    asr_weight, audio_weight, weight_analysis = self._analyze_query_for_weights(query)   # :632
+    query_embedding = _embedding_row(self.text_embedder.encode(query))                   # :635
+    batcher = getattr(self, "_cab_batcher", None)
+    if batcher is not None:           # shared library: this session's query rides in a batch with the others'
+        if self._cab_library.n_synced != len(self.audio_segments):    # new segments: append between two batches
+            batcher.run_exclusive(lambda: self._cab_library.sync(self.audio_segments))
+        res = batcher.search(query_embedding, asr_weight, audio_weight, k=TOP_K, threshold=THRESHOLD)
+    else:
+        index = self._cab_library.sync(self.audio_segments)
+        res = index.search(query_embedding[None, :], asr_weight, audio_weight, k=TOP_K, threshold=THRESHOLD)
+    results = _materialise(self, res, 0, asr_weight, audio_weight)
     processing_time = time.time() - start_time
     self.stats["search_pipeline"].update(processing_time, success=len(results) > 0)      # :688-689
     weight_info = {"asr_weight": asr_weight, "audio_weight": audio_weight,
                    "analysis": weight_analysis, "query": query}       # :692-697
     return results, weight_info
+
+
+def _b200_search_many(self, queries: List[str]) -> List[Tuple[List[Dict], Dict]]:
+    """`search_with_fusion` for several query strings with ONE scan batch (one corpus pass per 4
+    queries; the tensor-core scan from 64 queries on a bf16 library): the list of what
+    `search_with_fusion(q)` returns for each q, stats updated once per query."""
+    if not self.audio_segments:
+        return [([], {}) for _ in queries]
+    if not queries:
+        return []
+    start_time = time.time()
+    analysed = [self._analyze_query_for_weights(q) for q in queries]                     # :632
+    vectors = np.stack([_embedding_row(v) for v in self.text_embedder.encode(list(queries))])   # :635, one forward
+    index = self._cab_library.sync(self.audio_segments)
+    res = index.search(vectors, [a[0] for a in analysed], [a[1] for a in analysed], k=TOP_K, threshold=THRESHOLD)
+    out = []
+    for qi, (query, (asr_weight, audio_weight, weight_analysis)) in enumerate(zip(queries, analysed)):
+        results = _materialise(self, res, qi, asr_weight, audio_weight)
+        out.append((results, {"asr_weight": asr_weight, "audio_weight": audio_weight,
+                              "analysis": weight_analysis, "query": query}))
+    share = (time.time() - start_time) / len(queries)
+    for results, _ in out:
+        self.stats["search_pipeline"].update(share, success=len(results) > 0)
+    return out
 
 
 def accelerate(search_system, dtype: str = "fp32", device: int = 0, columnar: bool = False):
@@ -188,6 +223,7 @@ def accelerate(search_system, dtype: str = "fp32", device: int = 0, columnar: bo
     if columnar and not isinstance(search_system.audio_segments, SegmentTable):
         search_system.audio_segments = SegmentTable.from_segments(search_system.audio_segments)
     search_system.search_with_fusion = types.MethodType(_b200_search_with_fusion, search_system)
+    search_system.search_many = types.MethodType(_b200_search_many, search_system)
     return search_system
 
 
@@ -229,6 +265,15 @@ class DualPipelineAudioSearch:
         return query_weights.analyze_query_for_weights(query)
 
     search_with_fusion = _b200_search_with_fusion
+    search_many = _b200_search_many
+
+    def enable_batching(self, max_batch: int = 256, max_wait_s: float = 0.0):
+        """Concurrent `search_with_fusion` calls (threads sharing this engine) are coalesced into
+        batched GPU calls by a SearchBatcher; returns it (call `.close()` to stop)."""
+        from .batcher import SearchBatcher
+        index = self._cab_library.sync(self.audio_segments)
+        self._cab_batcher = SearchBatcher(index, max_batch=max_batch, max_wait_s=max_wait_s)
+        return self._cab_batcher
 
     # -- beyond the reference: a library that outlives the session (SURVEY.md 8(f) ranks 1, 3) ---
     def save_library(self, path: str, audio: bool = True) -> None:

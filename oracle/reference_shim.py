@@ -169,6 +169,8 @@ class FakeEmbedder:
         self.table = {k: np.asarray(v, dtype=np.float32) for k, v in table.items()}
 
     def encode(self, text, **_kw):
+        if isinstance(text, (list, tuple)):          # SentenceTransformer.encode(list) -> [n, 384]
+            return np.stack([self.table[t] for t in text])
         return self.table[text].copy()
 
 

@@ -149,3 +149,45 @@ def test_columnar_library_gives_the_same_results_and_survives_a_session(search_c
     assert isinstance(conv.audio_segments, SegmentTable)
     results, info = conv.search_with_fusion(rec["text"])
     _check([{k: v for k, v in r.items() if k != "file"} for r in results], info, rec)
+
+
+def test_search_many_and_session_batching(search_cases):
+    """Beyond the reference: `search_many` (one scan batch for several query strings) and
+    concurrent `search_with_fusion` calls coalesced by a SearchBatcher must return exactly what
+    one `search_with_fusion` call per query returns."""
+    import threading
+    case = search_cases[1]
+    a, b, f, _ = synth.library(case["seed"], case["n_rows"], case["n_queries"], case["plants"], case["partial"])
+    q = synth.raw_queries(case["seed"], 0, case["n_queries"])
+    embedder = FakeEmbedder({r["text"]: q[r["qi"]] for r in case["queries"]})
+    eng = DualPipelineAudioSearch(text_embedder=embedder)
+    assert eng.search_many(["zzz"]) == [([], {})]
+    eng.audio_segments.extend(segments_from_arrays(a, b, f))
+    texts = [r["text"] for r in case["queries"]]
+    single = [eng.search_with_fusion(t) for t in texts]
+    calls = eng.stats["search_pipeline"].total_calls
+    many = eng.search_many(texts)
+    assert eng.stats["search_pipeline"].total_calls == calls + len(texts)
+    for (r1, i1), (r2, i2), rec in zip(single, many, case["queries"]):
+        _check(r2, i2, rec)
+        assert i1 == i2 and [x["segment_id"] for x in r1] == [x["segment_id"] for x in r2]
+        assert [x["fusion_score"] for x in r1] == [x["fusion_score"] for x in r2]
+
+    batcher = eng.enable_batching(max_batch=64, max_wait_s=0.01)
+    out = {}
+
+    def session(t):
+        out[t] = eng.search_with_fusion(texts[t % len(texts)])
+    threads = [threading.Thread(target=session, args=(t,)) for t in range(32)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert batcher.stats.requests == 32 and batcher.stats.batches < 32
+    for t, (results, info) in out.items():
+        _check(results, info, case["queries"][t % len(texts)])
+    more = segments_from_arrays(a[:5], b[:5], f[:5])              # ingest while batching: appended between two batches
+    eng.audio_segments.extend(more)
+    results, info = eng.search_with_fusion(texts[0])
+    assert len(eng._cab_library.index) == len(f) + 5 and info["query"] == texts[0]
+    batcher.close()
