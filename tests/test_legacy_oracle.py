@@ -122,3 +122,79 @@ def test_clean_search_oracle_matches_the_reference_live():
         assert [r["similarity"] for r in ref] == sims.tolist()     # same expression, same floats
         assert all(set(r) == set(db[0]) | {"similarity"} for r in ref)
     assert rs.clean_search("text", q[0], [], "asr") == []
+
+
+# ---- host logic of the two drop-ins with an oracle-backed fake index (no GPU) ----------------------
+class _FakeIndex:
+    def __init__(self, dtype="fp32", capacity=0, device=0):
+        self.a = np.zeros((0, 384), np.float32); self.b = np.zeros((0, 384), np.float32); self.f = np.zeros(0, np.uint8)
+        self.appends = 0
+
+    def __len__(self):
+        return len(self.f)
+
+    def append(self, asr, audio, flags):
+        audio = np.zeros_like(asr) if audio is None else audio
+        self.a, self.b, self.f = np.vstack([self.a, asr]), np.vstack([self.b, audio]), np.concatenate([self.f, flags])
+        self.appends += 1
+
+    def clear(self):
+        self.a, self.b, self.f = self.a[:0], self.b[:0], self.f[:0]
+
+    def pinned_scores(self, nq=1):
+        return np.empty((nq, len(self)), np.float32)
+
+    def score_all(self, queries, class_weights, out=None):
+        res = np.stack([no.class_weight_scores(q, self.a, self.b, self.f & 1, self.f & 2, self.f >> 2, class_weights)
+                        for q in np.atleast_2d(queries)])
+        if out is not None:
+            out[...] = res
+            return out
+        return res
+
+    def search(self, queries, w_asr, w_audio, k=10, threshold=0.1, path="auto"):
+        from multimodal_audio_search_b200.index import SearchResult
+        q = np.atleast_2d(queries)
+        o = no.search(q[0], self.a, self.b, self.f, w_asr, w_audio, k=k, threshold=threshold)
+        idx = np.full((1, k), -1, np.int64); idx[0, :len(o.indices)] = o.indices
+        z = np.zeros((1, k), np.float32)
+        return SearchResult(idx, np.zeros((1, k)), z, z, np.zeros((1, k), np.uint8), np.array([len(o.indices)], np.int32))
+
+
+def test_drop_in_host_logic_with_a_fake_index(monkeypatch):
+    monkeypatch.setattr(legacy, "SegmentIndex", _FakeIndex)
+    z, meta = _cases()
+    m = meta[0]
+    a, b, f, _ = synth.library(m["seed"], m["n_rows"], m["n_queries"], m["plants"], m["partial"])
+    q = synth.raw_queries(m["seed"], 0, m["n_queries"])
+    good = no.legacy_good_speech(m["seed"], m["n_rows"])
+    db = rs.legacy_database(a, b, (f & 1).astype(bool), (f & 2).astype(bool), good)
+    eng = legacy.UnifiedAudioSearch(sentence_model=rs.ListEmbedder({"q0": q[0], "q1": q[1]}))
+    assert eng.search("q0", [], "adaptive").shape == (0,)
+    grown = list(db[:200])
+    assert eng.search("q0", grown, "asr_only").shape == (200,)
+    grown.extend(db[200:])
+    for qi in range(2):
+        for strategy in ("asr_only", "caption_only", "adaptive"):
+            sims = eng.search(f"q{qi}", grown, strategy)
+            assert sims.dtype == np.float64 and np.abs(sims - z[f"{m['name']}/{qi}/{strategy}"]).max() <= TOL
+    assert eng._cab_database.index.appends == 2                       # incremental sync, no rebuild
+    eng.search("q0", list(db), "adaptive")                            # another list object: rebuilt
+    assert eng._cab_database.index.appends == 3 and len(eng._cab_database.index) == len(db)
+
+    # clean_audio_search.py drop-in
+    case = json.load(open(CLEAN_GOLD))[0]
+    a, c, mm, ha, hc, q, qm = no.clean_library(case["seed"], case["n_rows"], 2, case["plants"])
+    cdb = rs.clean_database(a, c, mm, ha, hc)
+    texts = {f"{r['mode']} {r['qi']}": (qm if r["mode"] == "combined" else q)[r["qi"]] for r in case["queries"]}
+    ceng = legacy.CleanAudioSearch(text_embedder=rs.FakeEmbedder(texts))
+    assert ceng.search_audio("asr 0", "asr") == []
+    ceng.audio_database.extend(cdb)
+    for r in case["queries"]:
+        got = ceng.search_audio(f"{r['mode']} {r['qi']}", r["mode"])
+        assert [int(x["segment_id"][4:]) for x in got] == r["indices"]
+        np.testing.assert_allclose([x["similarity"] for x in got], r["similarity"], atol=1e-6, rtol=0)
+    seg = dict(cdb[0]); seg["asr_embedding"] = 3.0 * cdb[0]["combined_embedding"]
+    ceng.audio_database.append(seg)
+    with pytest.raises(ValueError, match="unit-length"):
+        ceng.search_audio("asr 0", "asr")
