@@ -58,7 +58,8 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
         "sm__cycles_elapsed.avg", "smsp__cycles_active.avg"]
 traffic = {}
-REPORT_WORKLOAD = {"prof_gemv": "1m_fp32_q1_top10", "prof_gemm": "10m_bf16_q256_top100"}
+REPORT_WORKLOAD = {"prof_gemv": "1m_fp32_q1_top10", "prof_gemm": "10m_bf16_q256_top100",
+                   "prof_score_all": "score_all_10m_fp32"}
 for rep in sorted(f for f in os.listdir(OUT) if f.endswith(".ncu-rep")):
     r = subprocess.run(["ncu", "-i", os.path.join(OUT, rep), "--page", "raw", "--csv"], capture_output=True, text=True)
     rows = list(csv.reader(io.StringIO(r.stdout)))
