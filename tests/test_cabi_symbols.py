@@ -1,6 +1,7 @@
 """CPU-only: the C-ABI library builds, loads, and exports exactly what include/cab.h declares;
 without a GPU every entry point fails loudly (no CPU fallback)."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -76,3 +77,37 @@ def test_torch_extension_registers_ops(lib):
     if not torch.cuda.is_available():
         with pytest.raises(Exception):      # CPU tensors are rejected, nothing is computed on the host
             ops.search(0, torch.zeros(1, 384), torch.ones(1), torch.ones(1), 10, 0.1, 0)
+
+
+def test_header_is_plain_c_and_a_c_program_links(lib, tmp_path):
+    """include/cab.h must be usable from C (the boundary has no C++ or torch types): compile it as
+    C99 with -pedantic, and link a C program against libcab.so that calls only entry points which
+    do not need a GPU."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = os.path.join(root, "include", "cab.h")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only", "-x", "c", header], check=True)
+    src = tmp_path / "main.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <string.h>\n#include "cab.h"\n'
+        "int main(void) {\n"
+        "    cab_index *idx = NULL;\n"
+        "    if (cab_version() != CAB_VERSION) return 1;\n"
+        "    if (sizeof(cab_candidate) != 24) return 2;\n"
+        "    if (cab_index_create(128, CAB_F32, 0, 0, &idx) != CAB_ERR_INVALID || idx != NULL) return 3;   /* wrong dim */\n"
+        "    if (!strstr(cab_last_error(NULL), \"dim\")) return 4;\n"
+        "    if (cab_search(NULL, NULL, 0, NULL, NULL, 1, 10, 0.1, 0, NULL, NULL, NULL, NULL, NULL, NULL, 0, NULL) != CAB_ERR_INVALID) return 5;\n"
+        "    if (cab_score_all(NULL, NULL, 0, 1, NULL, NULL, 0, NULL) != CAB_ERR_INVALID) return 6;\n"
+        '    printf("%s\\n", cab_status_string(CAB_ERR_NO_DEVICE));\n'
+        "    return 0;\n}\n")
+    libdir = os.path.join(root, "multimodal_audio_search_b200")
+    exe = tmp_path / "main"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-lcab", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stderr)
+    assert "no CPU fallback" in out.stdout
