@@ -171,3 +171,50 @@ def test_bulk_table_materialises_in_constant_time(tmp_path):
     dt = time.perf_counter() - t0
     assert len(rows) == 10 and rows[0]["end_time"] - rows[0]["start_time"] == 10.0
     assert dt < 0.5, f"load + 10 records took {dt:.3f}s for {n} rows"
+
+
+def test_round_trip_property(tmp_path_factory):
+    """Any list of reference-shaped records (unicode texts, empty strings, missing audio, extra
+    JSON-able keys) survives extend -> save -> load, field by field."""
+    from hypothesis import given, settings, strategies as st
+    text = st.text(max_size=40)
+    record = st.fixed_dictionaries({
+        "start_time": st.floats(0, 1e6, allow_nan=False), "duration": st.floats(0, 30, allow_nan=False),
+        "asr_text": text, "audio_description": text, "asr_success": st.booleans(), "audio_success": st.booleans(),
+        "sample_rate": st.sampled_from([8000, 16000, 44100]), "n_audio": st.integers(0, 50),
+        "extra": st.one_of(st.none(), st.dictionaries(st.text(min_size=1, max_size=8).filter(lambda k: k not in RECORD_ORDER and k != "file"),
+                                                      st.one_of(st.integers(-5, 5), text), max_size=2)),
+    })
+    base = tmp_path_factory.mktemp("prop")
+    counter = [0]
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.lists(record, min_size=1, max_size=12), st.sampled_from([None, "clip.wav", "ünï.flac"]))
+    def run(specs, file):
+        segs = []
+        for i, s in enumerate(specs):
+            seg = {"segment_id": f"seg_{i}", "start_time": s["start_time"], "end_time": s["start_time"] + s["duration"],
+                   "duration": s["duration"], "asr_text": s["asr_text"], "asr_embedding": None, "asr_success": s["asr_success"],
+                   "audio_description": s["audio_description"], "audio_embedding": None, "audio_success": s["audio_success"],
+                   "audio_data": np.arange(s["n_audio"], dtype=np.float32) if s["n_audio"] else None,
+                   "sample_rate": s["sample_rate"]}
+            if s["extra"]:
+                seg.update(s["extra"])
+            segs.append(seg)
+        t = SegmentTable.from_segments(segs, file=file)
+        counter[0] += 1
+        path = str(base / f"t{counter[0]}.meta")
+        t.save(path)
+        u = SegmentTable.load(path)
+        assert len(u) == len(segs)
+        for i, seg in enumerate(segs):
+            r = u[i]
+            for k, v in seg.items():
+                if k in ("asr_embedding", "audio_embedding"):
+                    continue
+                if k == "audio_data":
+                    assert (r[k] is None) if v is None else np.array_equal(r[k], v)
+                else:
+                    assert r[k] == v, (k, r[k], v)
+            assert r.get("file") == file
+    run()
