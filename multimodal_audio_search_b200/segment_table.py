@@ -382,8 +382,10 @@ class SegmentTable(Sequence):
         if audio and int(audio_offs[-1]) > 0:
             atmp = path + ".audio.tmp"
             with open(atmp, "wb") as f:
-                if self._audio_blob is not None and int(base_offs[-1]) > 0:
-                    f.write(np.asarray(self._audio_blob[:int(base_offs[-1])], dtype="<f4").tobytes())
+                if self._audio_blob is not None:
+                    step = 16 << 20                             # samples per write: the loaded blob may not fit in RAM
+                    for lo in range(0, int(base_offs[-1]), step):
+                        f.write(np.asarray(self._audio_blob[lo:min(lo + step, int(base_offs[-1]))], dtype="<f4").tobytes())
                 for a in self._audio_tail:
                     if a is not None:
                         f.write(np.ascontiguousarray(a, dtype="<f4").tobytes())
