@@ -147,7 +147,14 @@ CAB_API int cab_index_file_info(const char *path, int *dim, int *dtype, int64_t 
  *   out_fusion float64 fusion_score  = eff_w_asr*asr_sim + eff_w_audio*audio_sim  (:667-670)
  *   out_asr / out_audio  float32 cosine similarities (:646, :651)
  *   out_flags  the row's CAB_FLAG_* byte (gives the effective weights of :656-664)
- *   out_count  [n_queries] number of results (< k when fewer rows pass the threshold). */
+ *   out_count  [n_queries] number of results (< k when fewer rows pass the threshold).
+ * A query holding NaN/Inf (sklearn raises ValueError for the reference): with host outputs the
+ * call fails with CAB_ERR_NONFINITE; with device outputs (nothing is read back, the call does
+ * not wait) that query gets out_count = -1 and no results, the other queries are unaffected.
+ * Stream contract: consecutive calls on one handle go to the same stream (or the caller orders
+ * the streams); a search is launched so that it may START before the previous search on that
+ * stream has finished (programmatic dependent launch) but never reads a device query before the
+ * kernel in front of it has completed -- unless option "queries_settled" is set. */
 CAB_API int cab_search(cab_index *idx, const float *queries, int queries_loc, const double *w_asr,
                const double *w_audio, int n_queries, int k, double threshold, int path,
                int64_t *out_index, double *out_fusion, float *out_asr, float *out_audio,
@@ -209,11 +216,23 @@ CAB_API int cab_search_sharded(cab_index *idx, const float *queries, int queries
                                int64_t *out_index, double *out_fusion, float *out_asr, float *out_audio,
                                uint8_t *out_flags, int32_t *out_count, int out_loc, void *stream);
 
+/* Diagnostic (option "stamp_exchange" = 1): %globaltimer stamps, in ns, of the last sharded
+ * searches whose merge ran inside the finalize kernel -- per search {scan complete, own epoch flag
+ * raised on every rank, all ranks' flags seen, results written}.  Copies up to max_rows rows of 4
+ * (oldest first) into `out` (host) and returns the number of rows copied (0 on error, with
+ * cab_last_error set).  Synchronises the device.  NOTE: returns a row count, not a cab_status. */
+CAB_API int cab_index_exchange_stamps(cab_index *idx, uint64_t *out, int max_rows);
+
 /* ---- tuning / introspection -------------------------------------------------------------- */
 /* Options: "gemv_unroll" (row-steps in flight per warp: 1/2/4/8, 0 = default),
  * "gemv_blocks_per_sm" (resident CTAs per SM, 0 = default), "gemv_query_tile" (queries scored per
  * corpus pass, 1/2/4, 0 = default 4), "gemv_batch", "gemm_min_queries",
- * "time_kernels", "sync_after_search"; unknown keys fail. */
+ * "time_kernels", "sync_after_search", "stamp_exchange";
+ * "queries_settled" = 1: the caller promises that DEVICE query buffers passed to a search were
+ * completely written before the previous search on this handle was issued (pre-computed query
+ * batches); the scan of search i+1 then streams the corpus while search i's finalize / exchange /
+ * merge is still in flight.  Default 0: a search waits for the kernel in front of it before it
+ * reads its query.  Unknown keys fail. */
 CAB_API int cab_index_set_option(cab_index *idx, const char *key, int64_t value);
 CAB_API int64_t cab_index_get_option(const cab_index *idx, const char *key);
 /* Kernels launched by this handle since creation (for bench.py's gpu_launches). */

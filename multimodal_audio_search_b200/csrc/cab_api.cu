@@ -25,6 +25,8 @@ bool gemm_path_available();
 void launch_gemm_scan(const ScanArgs &a, int sm_count, void *workspace, size_t workspace_bytes,
                       cudaStream_t s, std::string *err);
 size_t gemm_workspace_bytes(int n_queries, int k, int sm_count);
+const int32_t *gemm_levels(const void *workspace, int sm_count);
+float gemm_level_step();
 }  // namespace cab
 
 static thread_local std::string g_last_error;
@@ -49,7 +51,7 @@ struct cab_index {
     cab_candidate *d_cands = nullptr;    size_t sz_cands = 0;
     uint8_t *d_out = nullptr;      size_t d_out_bytes = 0;  // packed outputs
     uint8_t *d_gemm_ws = nullptr;  size_t d_gemm_ws_bytes = 0;
-    int *d_nonfinite = nullptr;
+    int *d_nonfinite = nullptr;              // set by the ingest / score_all kernels (rows, or a score_all query)
     unsigned int *d_counters = nullptr;     // [0..63] GEMV chunk tickets, [64..65] score_all tickets (zero between launches)
     // pinned host staging
     uint8_t *h_in = nullptr;  size_t h_in_bytes = 0;
@@ -63,6 +65,7 @@ struct cab_index {
     // options
     GemvConfig gemv{0, 0, 0, 0};
     int64_t opt_time_kernels = 0, opt_sync = 0, opt_gemm_min_queries = 64, opt_gemv_batch = 32;
+    int64_t opt_queries_settled = 0, opt_stamp_exchange = 0;
     int64_t opt_finalize_general = 0, opt_chunk_rows = 0;    // 0 = auto: 96 KB of corpus per chunk (fp32 32 rows, bf16 64), profiles/r01_gemv_chunk_sweep.md
     // peer-memory exchange (sharded search)
     int peer_world = 0, peer_rank = 0, peer_qcap = 0, peer_kcap = 0;
@@ -72,6 +75,8 @@ struct cab_index {
     uint32_t peer_epoch = 0;
     unsigned int *d_done = nullptr;
     int *d_status = nullptr;
+    unsigned long long *d_stamps = nullptr;          // [kStampRows][4] %globaltimer stamps of the last sharded searches
+    uint32_t stamp_calls = 0;
     unsigned int *d_host_done = nullptr;             // CTA counter for host-visible completion
     uint32_t host_epoch = 0;
     int64_t launches = 0;
@@ -105,6 +110,8 @@ static int fail(cab_index *idx, int code, const char *fmt, ...) {
     } while (0)
 
 static size_t elem_size(int dtype) { return dtype == CAB_BF16 ? 2 : 4; }
+static size_t align_up(size_t x, size_t a);
+constexpr int kStampRows = 64;
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int cab_version(void) { return CAB_VERSION; }
@@ -137,7 +144,7 @@ static int grow(cab_index *idx, int64_t new_cap) {
     CU(idx, cudaSetDevice(idx->device));
     cudaError_t e = cudaMalloc(&na, size_t(new_cap) * row_bytes);
     if (e == cudaSuccess) e = cudaMalloc(&nb, size_t(new_cap) * row_bytes);
-    if (e == cudaSuccess) e = cudaMalloc(&nf, size_t(new_cap));
+    if (e == cudaSuccess) e = cudaMalloc(&nf, align_up(size_t(new_cap), 16));     // the tensor-core epilogue reads flag WORDS
     if (e != cudaSuccess) {
         cudaFree(na); cudaFree(nb); cudaFree(nf); cudaGetLastError();
         return fail(idx, CAB_ERR_NOMEM, "cannot allocate %lld rows (%s)", (long long)new_cap, cudaGetErrorString(e));
@@ -205,7 +212,8 @@ int cab_index_destroy(cab_index *idx) {
     cudaFree(idx->d_out); cudaFree(idx->d_gemm_ws); cudaFree(idx->d_nonfinite); cudaFree(idx->d_rows); cudaFree(idx->d_counters); cudaFree(idx->d_scores);
     for (int r = 0; r < idx->peer_world; ++r)
         if (idx->peer_attached && r != idx->peer_rank && idx->peer_ptr[r]) cudaIpcCloseMemHandle(idx->peer_ptr[r]);
-    cudaFree(idx->d_peer); cudaFree(idx->d_done); cudaFree(idx->d_status); cudaFree(idx->d_host_done);
+    cudaFree(idx->d_peer); cudaFree(idx->d_done); cudaFree(idx->d_status); cudaFree(idx->d_host_done); cudaFree(idx->d_stamps);
+
     cudaFreeHost(idx->h_in); cudaFreeHost(idx->h_out); cudaFreeHost(idx->h_rows);
     if (idx->ev_in) cudaEventDestroy(idx->ev_in);
     if (idx->ev_t0) cudaEventDestroy(idx->ev_t0);
@@ -620,7 +628,6 @@ static int make_emit(cab_index *idx, int n_lists, int nq, int k, double threshol
     EmitArgs ea{};
     ea.n_lists = n_lists; ea.n_queries = nq; ea.k = k;
     ea.w_asr = idx->d_w64; ea.w_audio = idx->d_w64 + nq; ea.threshold = threshold;
-    ea.nonfinite = idx->d_nonfinite;
     const bool dev = out_loc == CAB_DEVICE;
     uint8_t *d = idx->d_out;
     if (!dev) {
@@ -631,6 +638,8 @@ static int make_emit(cab_index *idx, int n_lists, int nq, int k, double threshol
         ea.done_epoch = ++idx->host_epoch ? idx->host_epoch : ++idx->host_epoch;
         ea.done_counter = idx->d_host_done;
         *reinterpret_cast<volatile uint32_t *>(d + L.done) = 0u;
+        *reinterpret_cast<volatile int *>(d + L.nonfinite) = 0;          // a CTA whose query holds NaN/Inf stores 1
+        ea.nonfinite_out = reinterpret_cast<int *>(d + L.nonfinite);
     }
     ea.out_index = dev && out_index ? out_index : reinterpret_cast<int64_t *>(d + L.index);
     ea.out_fusion = dev && out_fusion ? out_fusion : reinterpret_cast<double *>(d + L.fusion);
@@ -638,7 +647,6 @@ static int make_emit(cab_index *idx, int n_lists, int nq, int k, double threshol
     ea.out_audio = dev && out_audio ? out_audio : reinterpret_cast<float *>(d + L.audio);
     ea.out_flags = dev && out_flags ? out_flags : d + L.flags;
     ea.out_count = dev && out_count ? out_count : reinterpret_cast<int32_t *>(d + L.count);
-    ea.nonfinite_out = reinterpret_cast<int *>(d + L.nonfinite);
     *out = ea;
     return CAB_OK;
 }
@@ -684,9 +692,17 @@ static int stage_params(cab_index *idx, const float *queries, int queries_loc, c
 struct UserOut {
     int64_t *index; double *fusion; float *asr; float *audio; uint8_t *flags; int32_t *count; int loc;
 };
+// Sharded search: where the finalize kernel pushes this shard's candidates; when the whole call is
+// one scan pass of few queries the merge of all shards' candidates rides in the same kernel.
+struct Sharded {
+    PeerPush pp;
+    bool fused;              // out: the finalize kernel waited for the world's flags and emitted the results
+};
+constexpr int kFusedMergeMaxQueries = 64;      // CTAs that spin on peer flags must all be co-resident (one per SM)
+
 static int run_local(cab_index *idx, const float *queries, int queries_loc, const double *w_asr,
                      const double *w_audio, int nq, int k, double threshold, int path,
-                     const UserOut *out, cab_candidate *cand_dst, const PeerPush *peer, cudaStream_t s) {
+                     const UserOut *out, cab_candidate *cand_dst, Sharded *sh, cudaStream_t s) {
     if (!queries || !w_asr || !w_audio) return fail(idx, CAB_ERR_INVALID, "queries / weights are null");
     if (queries_loc != CAB_HOST && queries_loc != CAB_DEVICE) return fail(idx, CAB_ERR_INVALID, "queries_loc");
     if (nq <= 0 || nq > CAB_MAX_QUERIES) return fail(idx, CAB_ERR_INVALID, "n_queries must be in 1..%d", CAB_MAX_QUERIES);
@@ -730,16 +746,27 @@ static int run_local(cab_index *idx, const float *queries, int queries_loc, cons
         idx->inline_w_valid = true; idx->inline_w64[0] = w_asr[0]; idx->inline_w64[1] = w_audio[0];
     } else if ((rc = stage_params(idx, queries, queries_loc, w_asr, w_audio, nq, s, &dq))) return rc;
 
+    const PeerPush *peer = sh ? &sh->pp : nullptr;
+    const bool fuse_merge = sh && out && nq <= batch && nq <= kFusedMergeMaxQueries && idx->size > 0;
+    const bool emit_here = out && (!sh || fuse_merge);             // the finalize kernel writes the results
+    if (sh) sh->fused = fuse_merge;
     EmitArgs ea{};
-    if (out && (rc = make_emit(idx, 1, nq, k, threshold, out->index, out->fusion, out->asr, out->audio,
-                               out->flags, out->count, out->loc, &ea))) return rc;
+    if (emit_here && (rc = make_emit(idx, fuse_merge ? peer->world : 1, nq, k, threshold, out->index, out->fusion,
+                                     out->asr, out->audio, out->flags, out->count, out->loc, &ea))) return rc;
     if (inl.use_weights) { ea.inline_weights = 1; ea.w64_asr = inl.w64_asr; ea.w64_audio = inl.w64_audio; }
+    if (fuse_merge) {
+        ea.cands = peer->bufs[peer->rank];
+        ea.wait_flags = peer->flags[peer->rank] + peer->parity * peer->world;
+        ea.wait_epoch = peer->epoch;
+        ea.status = idx->d_status;
+        if (idx->opt_stamp_exchange && idx->d_stamps) ea.stamps = idx->d_stamps + size_t(idx->stamp_calls++ % kStampRows) * 4;
+    }
     idx->timed = false;
-    cab_candidate *cands = cand_dst ? cand_dst : idx->d_cands;      // sharded search: straight into the caller's block
+    cab_candidate *cands = cand_dst ? cand_dst : idx->d_cands;      // cab_search_candidates: straight into the caller's block
     if (idx->size == 0) {
         // nothing to scan: every candidate slot is empty
         CU(idx, cudaMemsetAsync(cands, 0xFF, size_t(nq) * k * sizeof(cab_candidate), s));
-        if (out) { ea.cands = cands; launch_emit(ea, s); idx->launches += 1; CU(idx, cudaGetLastError()); }
+        if (emit_here) { ea.cands = cands; launch_emit(ea, s); idx->launches += 1; CU(idx, cudaGetLastError()); }
         if (peer) { PeerPush pp = *peer; pp.q0 = 0; pp.signal = 1; launch_peer_push(cands, nq, k, pp, s); idx->launches += 1; CU(idx, cudaGetLastError()); }
         return CAB_OK;
     }
@@ -750,7 +777,12 @@ static int run_local(cab_index *idx, const float *queries, int queries_loc, cons
     sa.select_threshold = float(threshold) - 1e-6f;
     sa.partial_keys = idx->d_partial_keys;
     sa.inl = inl;
-    sa.n_partials = n_partials; sa.nonfinite = idx->d_nonfinite; sa.work_counters = idx->d_counters; sa.chunk_rows = idx->opt_chunk_rows ? int(idx->opt_chunk_rows) : (idx->dtype == CAB_BF16 ? 64 : 32);
+    // A device query may have been written by the kernel right in front of the scan on the caller's
+    // stream: the scan then waits for its predecessor before its first global read.  A host query
+    // travels in the kernel arguments / through an ordinary memcpy, and "queries_settled" is the
+    // caller's promise that device queries were complete before the previous search was issued.
+    sa.wait_early = (queries_loc == CAB_DEVICE && !idx->opt_queries_settled) ? 1 : 0;
+    sa.n_partials = n_partials; sa.work_counters = idx->d_counters; sa.chunk_rows = idx->opt_chunk_rows ? int(idx->opt_chunk_rows) : (idx->dtype == CAB_BF16 ? 64 : 32);
     FinalizeArgs fa{};
     fa.inl = inl;
     fa.asr = idx->asr; fa.audio = idx->audio; fa.flags = idx->flags; fa.dtype = idx->dtype;
@@ -759,6 +791,8 @@ static int run_local(cab_index *idx, const float *queries, int queries_loc, cons
     fa.slot_stride = use_gemm ? kGemmListCap : k;
     fa.work_counters = use_gemm ? nullptr : idx->d_counters;
     fa.counts = use_gemm ? reinterpret_cast<const int32_t *>(idx->d_gemm_ws) : nullptr;
+    fa.levels = use_gemm ? gemm_levels(idx->d_gemm_ws, idx->sm_count) : nullptr;
+    fa.select_threshold = sa.select_threshold; fa.level_step = gemm_level_step();
 
     if (idx->opt_time_kernels) CU(idx, cudaEventRecord(idx->ev_t0, s));
     for (int q0 = 0; q0 < nq; q0 += batch) {
@@ -775,21 +809,21 @@ static int run_local(cab_index *idx, const float *queries, int queries_loc, cons
             launch_gemv_scan(sa, plan, s);
         }
         if (idx->opt_time_kernels && q0 + batch >= nq) CU(idx, cudaEventRecord(idx->ev_t1, s));
-        fa.queries = sa.queries; fa.n_queries = m; fa.cands = cands + size_t(q0) * k;
+        fa.queries = sa.queries; fa.n_queries = m; fa.cands = peer ? nullptr : cands + size_t(q0) * k;
         if (peer) { fa.peer = *peer; fa.peer.q0 = q0; fa.peer.signal = q0 + batch >= nq ? 1 : 0; }
-        if (out) {
+        if (emit_here) {
             EmitArgs eb = ea;                           // this batch's slice of the outputs
             eb.n_queries = m;
             eb.w_asr = ea.w_asr + q0; eb.w_audio = ea.w_audio + q0;
             eb.out_index = ea.out_index + size_t(q0) * k; eb.out_fusion = ea.out_fusion + size_t(q0) * k;
             eb.out_asr = ea.out_asr + size_t(q0) * k; eb.out_audio = ea.out_audio + size_t(q0) * k;
             eb.out_flags = ea.out_flags + size_t(q0) * k; eb.out_count = ea.out_count + q0;
-            if (q0 + batch < nq) { eb.nonfinite_out = nullptr; eb.done_epoch = 0; }   // only the last batch reports / signals
+            if (q0 + batch < nq) eb.done_epoch = 0;                                   // only the last batch signals completion
             launch_finalize(fa, &eb, s);
         } else {
             launch_finalize(fa, nullptr, s);
         }
-        idx->launches += 2;
+        idx->launches += use_gemm ? 3 : 2;          // (prologue +) scan + finalize
     }
     if (idx->opt_time_kernels) idx->timed = true;
     CU(idx, cudaGetLastError());
@@ -821,11 +855,8 @@ static int finish_outputs(cab_index *idx, int nq, int k, const UserOut &o, cudaS
     }
     std::atomic_thread_fence(std::memory_order_acquire);
     idx->ev_in_pending = false;
-    if (*reinterpret_cast<const volatile int *>(h + L.nonfinite)) {
-        CU(idx, cudaMemsetAsync(idx->d_nonfinite, 0, sizeof(int), s));
-        CU(idx, cudaStreamSynchronize(s));
+    if (*reinterpret_cast<const volatile int *>(h + L.nonfinite))
         return fail(idx, CAB_ERR_NONFINITE, "Input contains NaN or infinity (query)");
-    }
     const size_t n = size_t(nq) * k;
     if (o.index) memcpy(o.index, h + L.index, n * 8);
     if (o.fusion) memcpy(o.fusion, h + L.fusion, n * 8);
@@ -964,6 +995,8 @@ int cab_peer_init(cab_index *idx, int rank, int world, int max_queries, int max_
     CU(idx, cudaMemset(idx->d_done, 0, sizeof(unsigned int)));
     CU(idx, cudaMalloc((void **)&idx->d_status, sizeof(int)));
     CU(idx, cudaMemset(idx->d_status, 0, sizeof(int)));
+    CU(idx, cudaMalloc((void **)&idx->d_stamps, size_t(kStampRows) * 4 * sizeof(unsigned long long)));
+    CU(idx, cudaMemset(idx->d_stamps, 0, size_t(kStampRows) * 4 * sizeof(unsigned long long)));
     CU(idx, cudaDeviceSynchronize());
     cudaIpcMemHandle_t h;
     CU(idx, cudaIpcGetMemHandle(&h, idx->d_peer));
@@ -997,9 +1030,11 @@ int cab_search_sharded(cab_index *idx, const float *queries, int queries_loc, co
     if (!idx->peer_attached) return fail(idx, CAB_ERR_INVALID, "cab_peer_init / cab_peer_attach first");
     if (n_queries > idx->peer_qcap || k > idx->peer_kcap)
         return fail(idx, CAB_ERR_INVALID, "n_queries / k exceed the exchange buffer (%d x %d)", idx->peer_qcap, idx->peer_kcap);
+    if (out_loc != CAB_HOST && out_loc != CAB_DEVICE) return fail(idx, CAB_ERR_INVALID, "out_loc");
     cudaStream_t s = stream ? (cudaStream_t)stream : idx->own_stream;
     const uint32_t epoch = ++idx->peer_epoch;
-    PeerPush pp{};
+    Sharded sh{};
+    PeerPush &pp = sh.pp;
     pp.world = idx->peer_world; pp.rank = idx->peer_rank; pp.parity = int(epoch & 1u); pp.epoch = epoch;
     pp.n_queries_total = n_queries; pp.done_counter = idx->d_done;
     const size_t half = peer_half_elems(idx);
@@ -1007,22 +1042,41 @@ int cab_search_sharded(cab_index *idx, const float *queries, int queries_loc, co
         pp.flags[r] = reinterpret_cast<uint32_t *>(idx->peer_ptr[r]);
         pp.bufs[r] = reinterpret_cast<cab_candidate *>(idx->peer_ptr[r] + peer_flags_bytes()) + size_t(pp.parity) * half;
     }
-    int rc = run_local(idx, queries, queries_loc, w_asr, w_audio, n_queries, k, threshold, path, nullptr, nullptr, &pp, s);
-    if (rc != CAB_OK) return rc;
     const UserOut o{out_index, out_fusion, out_asr, out_audio, out_flags, out_count, out_loc};
-    if (out_loc != CAB_HOST && out_loc != CAB_DEVICE) return fail(idx, CAB_ERR_INVALID, "out_loc");
-    EmitArgs ea{};
-    if ((rc = make_emit(idx, idx->peer_world, n_queries, k, threshold, out_index, out_fusion, out_asr,
-                        out_audio, out_flags, out_count, out_loc, &ea))) return rc;
-    ea.cands = pp.bufs[idx->peer_rank];
-    if (n_queries == 1 && idx->inline_w_valid) { ea.inline_weights = 1; ea.w64_asr = idx->inline_w64[0]; ea.w64_audio = idx->inline_w64[1]; }
-    ea.wait_flags = pp.flags[idx->peer_rank] + pp.parity * idx->peer_world;
-    ea.wait_epoch = epoch;
-    ea.status = idx->d_status;
-    launch_emit(ea, s);
-    idx->launches += 1;
-    CU(idx, cudaGetLastError());
+    int rc = run_local(idx, queries, queries_loc, w_asr, w_audio, n_queries, k, threshold, path, &o, nullptr, &sh, s);
+    if (rc != CAB_OK) return rc;
+    if (!sh.fused) {
+        // many queries / several scan passes / an empty shard: the merge is its own launch
+        EmitArgs ea{};
+        if ((rc = make_emit(idx, idx->peer_world, n_queries, k, threshold, out_index, out_fusion, out_asr,
+                            out_audio, out_flags, out_count, out_loc, &ea))) return rc;
+        ea.cands = pp.bufs[idx->peer_rank];
+        if (n_queries == 1 && idx->inline_w_valid) { ea.inline_weights = 1; ea.w64_asr = idx->inline_w64[0]; ea.w64_audio = idx->inline_w64[1]; }
+        ea.wait_flags = pp.flags[idx->peer_rank] + pp.parity * idx->peer_world;
+        ea.wait_epoch = epoch;
+        ea.status = idx->d_status;
+        launch_emit(ea, s);
+        idx->launches += 1;
+        CU(idx, cudaGetLastError());
+    }
     return finish_outputs(idx, n_queries, k, o, s);
+}
+
+int cab_index_exchange_stamps(cab_index *idx, uint64_t *out, int max_rows) {
+    CHECK_HANDLE(idx);
+    if (!out || max_rows < 0) return fail(idx, CAB_ERR_INVALID, "bad stamp buffer");
+    if (!idx->d_stamps) return 0;
+    CU(idx, cudaSetDevice(idx->device));
+    const int have = int(std::min<uint32_t>(idx->stamp_calls, kStampRows));
+    const int n = std::min(have, max_rows);
+    std::vector<unsigned long long> all(size_t(kStampRows) * 4);
+    CU(idx, cudaDeviceSynchronize());
+    CU(idx, cudaMemcpy(all.data(), idx->d_stamps, all.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) {                    // oldest first among the last n
+        const uint32_t call = idx->stamp_calls - uint32_t(n) + uint32_t(i);
+        memcpy(out + size_t(i) * 4, all.data() + size_t(call % kStampRows) * 4, 4 * sizeof(uint64_t));
+    }
+    return n;
 }
 
 int cab_index_set_option(cab_index *idx, const char *key, int64_t value) {
@@ -1036,6 +1090,8 @@ int cab_index_set_option(cab_index *idx, const char *key, int64_t value) {
     else if (k == "time_kernels") idx->opt_time_kernels = value != 0;
     else if (k == "sync_after_search") idx->opt_sync = value != 0;
     else if (k == "finalize_general") idx->opt_finalize_general = value != 0;
+    else if (k == "queries_settled") idx->opt_queries_settled = value != 0;
+    else if (k == "stamp_exchange") { idx->opt_stamp_exchange = value != 0; idx->stamp_calls = 0; }
     else if (k == "gemv_chunk_rows") { if (value < 0 || value > 4096) return fail(idx, CAB_ERR_INVALID, "gemv_chunk_rows in 0..4096 (0 = auto)"); idx->opt_chunk_rows = value; }
     else if (k == "gemm_min_queries") { if (value < 1) return fail(idx, CAB_ERR_INVALID, "gemm_min_queries >= 1"); idx->opt_gemm_min_queries = value; }
     else if (k == "gemv_batch") { if (value < 1 || value > 64) return fail(idx, CAB_ERR_INVALID, "gemv_batch in 1..64"); idx->opt_gemv_batch = value; }
@@ -1052,6 +1108,8 @@ int64_t cab_index_get_option(const cab_index *idx, const char *key) {
     if (k == "time_kernels") return idx->opt_time_kernels;
     if (k == "sync_after_search") return idx->opt_sync;
     if (k == "finalize_general") return idx->opt_finalize_general;
+    if (k == "queries_settled") return idx->opt_queries_settled;
+    if (k == "stamp_exchange") return idx->opt_stamp_exchange;
     if (k == "gemv_chunk_rows") return idx->opt_chunk_rows;
     if (k == "gemm_min_queries") return idx->opt_gemm_min_queries;
     if (k == "gemv_batch") return idx->opt_gemv_batch;

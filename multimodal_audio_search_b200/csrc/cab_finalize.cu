@@ -3,7 +3,12 @@
 // (2) emit -- from 1..world candidate lists per query compute the reference's float64 fusion
 // score (audio_search.py:656-670), apply the strict float64 threshold (:672), order by
 // (score desc, global index asc) (:685) and write the first k (:699).
-// On a single GPU (one candidate list) emit runs inside the finalize kernel.
+// On a single GPU (one candidate list) emit runs inside the finalize kernel.  Sharded search
+// (corpus split over ranks): the finalize kernel stores its candidates straight into every rank's
+// exchange buffer over NVLink peer memory, raises its epoch flag on every rank, waits for the
+// world's flags and merges -- ONE kernel per search after the scan.  Before it touches the
+// exchange it releases its dependents (griddepcontrol.launch_dependents), so the next search's
+// scan streams the corpus while this search's exchange and merge are still in flight.
 //
 // Both touch O(k) rows per query; they are latency-, not bandwidth-bound, and run as one CTA per
 // query: every global load is issued in parallel (no dependent chains), all selection happens in
@@ -80,19 +85,37 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
 __device__ __forceinline__ size_t peer_slot(const PeerPush &p, int q, int k, int i) {
     return (size_t(p.rank) * p.n_queries_total + q) * k + i;
 }
-// After every CTA of the (last) launch has stored its candidates on all ranks: raise this rank's
-// epoch flag on every rank.  Called by all threads of every CTA.
-__device__ __forceinline__ void peer_signal(const PeerPush &p) {
-    __threadfence_system();                       // this thread's peer stores are performed system-wide
-    __syncthreads();
-    if (threadIdx.x == 0 && p.signal) {
-        const unsigned prev = atomicAdd(p.done_counter, 1u);
-        if (prev == gridDim.x - 1) {              // last CTA: everyone's stores are ordered before this
-            *p.done_counter = 0u;
-            __threadfence_system();
-            for (int r = 0; r < p.world; ++r) st_release_sys(p.flags[r] + p.parity * p.world + p.rank, p.epoch);
-        }
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Store `n` candidates (shared memory) of query q into every rank's exchange buffer and, once
+// every CTA of the (last) launch has done so, raise this rank's epoch flag on every rank.
+// Thread t stores candidate t % k on rank t / k: all world x k records leave in parallel.  Only the
+// storing threads pay the system-scope fence; the release store of the flag orders the rest.
+// Called by all threads of the CTA.
+__device__ __forceinline__ void peer_push_and_signal(const PeerPush &p, const cab_candidate *cand, int q, int k,
+                                                     int *s_last) {
+    for (int t = threadIdx.x; t < p.world * k; t += blockDim.x) {
+        const int r = t / k, i = t - r * k;
+        p.bufs[r][peer_slot(p, q, k, i)] = cand[i];
+        __threadfence_system();                   // this thread's peer store is performed system-wide
     }
+    __syncthreads();
+    if (!p.signal) return;
+    if (gridDim.x > 1) {                          // several queries: the last CTA to finish raises the flags
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const unsigned prev = atomicAdd(p.done_counter, 1u);
+            *s_last = prev == gridDim.x - 1;
+            if (*s_last) *p.done_counter = 0u;
+        }
+        __syncthreads();
+        if (!*s_last) return;
+    }
+    if (threadIdx.x < p.world) st_release_sys(p.flags[threadIdx.x] + p.parity * p.world + p.rank, p.epoch);
 }
 
 // Host-visible completion of a launch whose outputs live in mapped pinned host memory: called by
@@ -111,6 +134,23 @@ __device__ __forceinline__ void host_signal(const EmitArgs &e) {
     }
 }
 
+// Wait until the epoch flags of all `n_lists` ranks hold `epoch` (their candidates of this search
+// have landed in our exchange buffer).  Bounded: a rank that never arrives is an error, not a hang.
+__device__ __forceinline__ void wait_peer_flags(const uint32_t *flags, int n_lists, uint32_t epoch, int *status) {
+    if (threadIdx.x < n_lists) {
+        const long long t0 = clock64();
+        while (ld_acquire_sys(flags + threadIdx.x) != epoch) {
+            if (clock64() - t0 > 20000000000ll) {              // ~10 s
+                if (status) atomicExch(status, 7);
+                __threadfence_system();
+                asm volatile("trap;");
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// Used when there was nothing to scan (empty shard): push a prepared candidate block.
 __global__ void __launch_bounds__(256) peer_push_kernel(const cab_candidate *__restrict__ local, int n_queries, int k, PeerPush p) {
     const int total = n_queries * k;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
@@ -118,10 +158,80 @@ __global__ void __launch_bounds__(256) peer_push_kernel(const cab_candidate *__r
         const size_t slot = peer_slot(p, p.q0 + t / k, k, t % k);
         for (int r = 0; r < p.world; ++r) p.bufs[r][slot] = c;
     }
-    peer_signal(p);
+    __threadfence_system();
+    __syncthreads();
+    if (p.signal && threadIdx.x < p.world) st_release_sys(p.flags[threadIdx.x] + p.parity * p.world + p.rank, p.epoch);
 }
 void launch_peer_push(const cab_candidate *local, int n_queries, int k, const PeerPush &peer, cudaStream_t s) {
     peer_push_kernel<<<1, 256, 0, s>>>(local, n_queries, k, peer);
+}
+
+// ---- emit: rank one query's candidates and write the first k ------------------------------------------
+// `cand_at(t)` returns candidate t of n_cand (<= blockDim.x, <= kEmitMax).  score/index/pos are
+// shared arrays of kEmitMax entries.  Order: (float64 fusion desc, global index asc) = Python's
+// stable descending sort (:685).  Few candidates are ranked by counting (no barriers), many by a
+// block bitonic sort.  Called by all threads of the CTA.
+constexpr int kEmitMax = 1024;      // >= world(8) x CAB_MAX_K(128)
+constexpr int kEmitCountMax = 256;
+
+template <typename CandAt>
+__device__ __forceinline__ void emit_ranked(CandAt cand_at, int n_cand, int qi, const EmitArgs &e, bool bad_query,
+                                            uint64_t *score, int64_t *index, uint16_t *pos) {
+    const double wa = e.inline_weights ? e.w64_asr : e.w_asr[qi], wb = e.inline_weights ? e.w64_audio : e.w_audio[qi];
+    const int t = threadIdx.x;
+    const size_t o0 = size_t(qi) * e.k;
+    auto write = [&](int slot, const cab_candidate &c, uint64_t sc) {
+        e.out_index[o0 + slot] = c.index;
+        e.out_fusion[o0 + slot] = unorderable64(sc);
+        e.out_asr[o0 + slot] = c.asr_sim;
+        e.out_audio[o0 + slot] = c.audio_sim;
+        e.out_flags[o0 + slot] = uint8_t(c.flags);
+    };
+    cab_candidate c{};
+    uint64_t sc = 0ull;
+    int64_t gi = INT64_MAX;
+    if (t < n_cand) {
+        c = cand_at(t);
+        bad_query |= (t == 0 && c.index == kBadQueryIndex);
+        sc = reference_fusion(c, wa, wb, e.threshold);
+        if (sc) gi = c.index;
+    }
+    bad_query = __syncthreads_or(bad_query);
+    if (bad_query) sc = 0ull;
+    int n_res;
+    if (n_cand <= kEmitCountMax) {
+        if (t < n_cand) { score[t] = sc; index[t] = gi; }
+        n_res = __syncthreads_count(sc != 0ull);
+        if (sc != 0ull) {
+            int rank = 0;
+            for (int j = 0; j < n_cand; ++j) {
+                const uint64_t sj = score[j];
+                rank += (sj > sc) || (sj == sc && index[j] < gi);
+            }
+            if (rank < e.k) write(rank, c, sc);
+        }
+        if (n_res > e.k) n_res = e.k;
+    } else {
+        int np2 = 512;
+        while (np2 < n_cand) np2 <<= 1;
+        for (int i = t; i < np2; i += blockDim.x) {
+            score[i] = i == t ? sc : 0ull; index[i] = i == t ? gi : INT64_MAX; pos[i] = uint16_t(i);
+        }
+        block_sort_results(score, index, pos, np2);
+        n_res = __syncthreads_count(t < e.k && score[t] != 0ull);
+        if (t < e.k && score[t] != 0ull) write(t, cand_at(pos[t]), score[t]);
+    }
+    for (int i = n_res + t; i < e.k; i += blockDim.x) {                 // pad beyond the results
+        e.out_index[o0 + i] = -1;
+        e.out_fusion[o0 + i] = 0.0;
+        e.out_asr[o0 + i] = 0.f;
+        e.out_audio[o0 + i] = 0.f;
+        e.out_flags[o0 + i] = 0;
+    }
+    if (t == 0) {
+        e.out_count[qi] = bad_query ? -1 : n_res;
+        if (bad_query && e.nonfinite_out) *e.nonfinite_out = 1;
+    }
 }
 
 // ---- finalize ---------------------------------------------------------------------------------
@@ -133,6 +243,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, E
     __shared__ uint64_t s_head[kMaxHeads];
     __shared__ float s_q[kDim];
     __shared__ int s_cnt;
+    __shared__ int s_last;
     __shared__ uint64_t s_bound;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -140,6 +251,8 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, E
     // Launched with programmatic stream serialization: the CTA is already resident when the scan
     // finishes; everything the scan wrote is visible after this wait.
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    const bool stamp = e.stamps && qi == 0 && threadIdx.x == 0;
+    if (stamp) e.stamps[0] = globaltimer_ns();
     if (threadIdx.x == 0) { s_cnt = 0; s_bound = 0ull; if (a.work_counters) a.work_counters[qi] = 0u; }
     if (a.inl.use_query && threadIdx.x < kDim) s_q[threadIdx.x] = a.inl.q[threadIdx.x];   // kernel-argument query
     __syncthreads();
@@ -163,7 +276,8 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, E
     const int total = a.n_partials * a.slot_stride;
     const int32_t *__restrict__ counts = a.counts ? a.counts + size_t(qi) * a.n_partials : nullptr;
 
-    // Warp-aggregated append of passing keys into s_sort; returns false if the buffer overflowed.
+    // Warp-aggregated append of passing keys into s_sort (keys beyond the buffer are dropped; every
+    // caller either bounds the number of survivors beforehand or checks s_cnt afterwards).
     auto append = [&](bool pass, uint64_t key) {
         const unsigned m = __ballot_sync(kFull, pass);
         if (m == 0) return;
@@ -172,6 +286,28 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, E
         base = __shfl_sync(kFull, base, 0);
         const int pos = base + __popc(m & ((1u << lane) - 1u));
         if (pass && pos < kSortCap) s_sort[pos] = key;
+    };
+    // Rank the S <= kRankMax keys in s_sort by counting and leave the best k sorted in s_sort[0..k).
+    auto rank_by_counting = [&](int S) {
+        uint64_t mine[kRankMax / kFinThreads];
+        int rank[kRankMax / kFinThreads];
+#pragma unroll
+        for (int u = 0; u < kRankMax / kFinThreads; ++u) {
+            const int i = threadIdx.x + u * kFinThreads;
+            mine[u] = i < S ? s_sort[i] : 0ull;
+            rank[u] = 0;
+        }
+        for (int t = 0; t < S; ++t) {
+            const uint64_t x = s_sort[t];
+#pragma unroll
+            for (int u = 0; u < kRankMax / kFinThreads; ++u) rank[u] += x > mine[u];
+        }
+        __syncthreads();                                         // all reads of s_sort done
+#pragma unroll
+        for (int u = 0; u < kRankMax / kFinThreads; ++u)
+            if (threadIdx.x + u * kFinThreads < S && rank[u] < a.k) s_sort[rank[u]] = mine[u];
+        if (threadIdx.x == 0) s_cnt = S < a.k ? S : a.k;
+        __syncthreads();
     };
 
     // ---- fast path (small k): each scan CTA's slots are sorted, so the k-th largest list HEAD is
@@ -197,25 +333,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, E
         __syncthreads();
         const int S = s_cnt;
         if (S <= kRankMax) {
-            uint64_t mine[kRankMax / kFinThreads];
-            int rank[kRankMax / kFinThreads];
-#pragma unroll
-            for (int u = 0; u < kRankMax / kFinThreads; ++u) {
-                const int i = threadIdx.x + u * kFinThreads;
-                mine[u] = i < S ? s_sort[i] : 0ull;
-                rank[u] = 0;
-            }
-            for (int t = 0; t < S; ++t) {
-                const uint64_t x = s_sort[t];
-#pragma unroll
-                for (int u = 0; u < kRankMax / kFinThreads; ++u) rank[u] += x > mine[u];
-            }
-            __syncthreads();                                         // all reads of s_sort done
-#pragma unroll
-            for (int u = 0; u < kRankMax / kFinThreads; ++u)
-                if (threadIdx.x + u * kFinThreads < S && rank[u] < a.k) s_sort[rank[u]] = mine[u];
-            if (threadIdx.x == 0) s_cnt = S < a.k ? S : a.k;
-            __syncthreads();
+            rank_by_counting(S);
             done = true;
         } else {
             __syncthreads();
@@ -224,17 +342,73 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, E
         }
     }
 
-    // ---- counted lists (tensor-core scan): lists are mostly empty (tens of entries in 256 slots),
-    // so index the VALID entries through a prefix sum of the counts instead of walking every slot.
+    // ---- counted lists (tensor-core scan), fast path: the scan's per-query score-level histogram
+    // gives a bound -- the lower edge of the highest level L at or above which >= k candidates were
+    // pushed -- that at most suffix(L) keys exceed.  If that fits the ranking buffer, each warp
+    // walks whole lists (coalesced, only the valid entries) and the survivors are ranked by
+    // counting: no sort, two barriers.
+    if (!done && counts && a.levels && !a.force_general) {
+        int *s_lv = reinterpret_cast<int *>(s_head);                   // s_head is unused on this path
+        if (threadIdx.x < 64) s_lv[threadIdx.x] = a.levels[size_t(qi) * 64 + threadIdx.x];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int suffix = 0, lvl = 0, above = 0;
+            for (int j = 63; j >= 0; --j) { suffix += s_lv[j]; if (suffix >= a.k) { lvl = j; break; } }
+            above = suffix;                                            // candidates ever pushed at levels >= lvl
+            if (suffix < a.k) { lvl = -1; }                            // fewer than k candidates at all: keep everything
+            s_lv[64] = above;
+            s_bound = lvl > 0 ? bound_key(a.select_threshold + float(lvl) * a.level_step - 2e-6f) : 0ull;
+        }
+        __syncthreads();
+        if (s_lv[64] <= kRankMax) {
+            const uint64_t bound = s_bound;
+            for (int l = warp; l < a.n_partials; l += kFinWarps) {
+                int c = counts[l];
+                c = c < a.slot_stride ? c : a.slot_stride;
+                const uint64_t *lp = slots + size_t(l) * a.slot_stride;
+                for (int i = lane; i < ((c + 31) & ~31); i += 32) {
+                    const uint64_t key = i < c ? lp[i] : 0ull;
+                    append(key > bound, key);
+                }
+            }
+            __syncthreads();
+            const int S = s_cnt;
+            if (S <= kRankMax) {                                       // always (S <= suffix(L)); checked anyway
+                rank_by_counting(S);
+                done = true;
+            } else {
+                __syncthreads();
+                if (threadIdx.x == 0) { s_cnt = 0; s_bound = 0ull; }
+                __syncthreads();
+            }
+        } else {
+            __syncthreads();
+            if (threadIdx.x == 0) s_bound = 0ull;
+            __syncthreads();
+        }
+    }
+
+    // ---- counted lists, general path: index the VALID entries through a prefix sum of the counts,
+    // stream them through the buffer, sort + trim whenever it fills ---------------------------------
     if (!done && counts) {
-        int *s_pref = reinterpret_cast<int *>(s_head);                 // s_head is unused on this path
+        int *s_pref = reinterpret_cast<int *>(s_head);
         const int P = a.n_partials < 2 * kMaxHeads - 1 ? a.n_partials : 2 * kMaxHeads - 1;
         for (int j = threadIdx.x; j < P; j += kFinThreads) {
             const int c = counts[j];
             s_pref[j + 1] = c < a.slot_stride ? c : a.slot_stride;
         }
         __syncthreads();
-        if (threadIdx.x == 0) { s_pref[0] = 0; for (int j = 0; j < P; ++j) s_pref[j + 1] += s_pref[j]; }
+        if (warp == 0) {                                               // inclusive scan, 32 lists per step
+            int carry = 0;
+            for (int j0 = 0; j0 < P; j0 += 32) {
+                int v = j0 + lane < P ? s_pref[j0 + lane + 1] : 0;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(kFull, v, o); if (lane >= o) v += n; }
+                if (j0 + lane < P) s_pref[j0 + lane + 1] = v + carry;
+                carry += __shfl_sync(kFull, v, 31);
+            }
+            if (lane == 0) s_pref[0] = 0;
+        }
         __syncthreads();
         const int T = s_pref[P];
         for (int base = 0; base < T; base += kFinThreads * kFinUnroll) {
@@ -281,16 +455,23 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, E
         }
         trim();
     }
-    const int n_win = s_cnt;
+    int n_win = s_cnt;
+
+    // Everything the next scan on this stream touches -- its ticket counters (reset above), the
+    // partial-key slots, counts and levels (all consumed into shared memory by now) -- is released:
+    // let the dependent grid start while this one re-scores, exchanges and merges.
+    __threadfence();
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     // ---- re-score the winners: one lane group per row, same operation order as the scan ---------
     float q[TR::NQ];
     const float *qsrc = a.queries + size_t(qi) * kDim;
-    load_query<DT>([&](int i) { return a.inl.use_query ? s_q[i] : qsrc[i]; }, lane, q);
+    const bool finite = load_query<DT>([&](int i) { return a.inl.use_query ? s_q[i] : qsrc[i]; }, lane, q);
+    if (!finite) n_win = 0;                                // NaN/Inf query: no results, reported below
     const int g = lane & (TR::G - 1), sub = lane / TR::G;
     const uint4 *__restrict__ A = reinterpret_cast<const uint4 *>(a.asr);
     const uint4 *__restrict__ B = reinterpret_cast<const uint4 *>(a.audio);
-    cab_candidate *out = a.cands + size_t(qi) * a.k;
+    cab_candidate *out = a.cands ? a.cands + size_t(qi) * a.k : nullptr;
     for (int i0 = warp * TR::RW; i0 < a.k; i0 += kFinWarps * TR::RW) {
         const int i = i0 + sub;
         const bool have = i < n_win;                       // uniform within a lane group
@@ -309,58 +490,46 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, E
         sb = group_sum<DT>(sb);
         if (g == 0 && i < a.k) {
             cab_candidate c;
-            c.index = have ? a.row_base + int64_t(row) : int64_t(-1);
+            c.index = have ? a.row_base + int64_t(row) : (finite ? int64_t(-1) : kBadQueryIndex);
             c.asr_sim = sa; c.audio_sim = sb;
             c.flags = have ? uint32_t(a.flags[row]) : 0u;
             c.pad = 0u;
-            out[i] = c;
+            if (out) out[i] = c;
             s_cand[i] = c;
-            if (a.peer.world) {                            // sharded search: store on every rank over NVLink
-                const size_t slot = peer_slot(a.peer, a.peer.q0 + qi, a.k, i);
-                for (int r = 0; r < a.peer.world; ++r) a.peer.bufs[r][slot] = c;
-            }
         }
     }
-    if (a.peer.world) peer_signal(a.peer);
-    if (!e.out_index) return;          // sharded search: candidates go to the exchange
+    __syncthreads();
+    uint64_t *score = s_sort;                                        // the selection buffer is free now
+    int64_t *index = reinterpret_cast<int64_t *>(s_sort + kEmitMax);
+    uint16_t *pos = reinterpret_cast<uint16_t *>(s_sort + 2 * kEmitMax);
+    if (a.peer.world) {
+        // sharded search: this shard's candidates go to every rank over NVLink peer memory
+        peer_push_and_signal(a.peer, s_cand, a.peer.q0 + qi, a.k, &s_last);
+        if (stamp) e.stamps[1] = globaltimer_ns();
+        if (!e.out_index) return;                                    // merged by a separate emit launch
+        wait_peer_flags(e.wait_flags, e.n_lists, e.wait_epoch, e.status);
+        if (stamp) e.stamps[2] = globaltimer_ns();
+        const cab_candidate *lists = e.cands;                        // [n_lists][n_queries][k], this rank's buffer
+        const int nq = e.n_queries, k = e.k;
+        emit_ranked([&](int t) {
+            const int list = t / k, i = t - list * k;
+            const cab_candidate *p = lists + (size_t(list) * nq + qi) * k + i;
+            cab_candidate c;                                         // L2 loads: the records were written by peers
+            const longlong2 lo = __ldcg(reinterpret_cast<const longlong2 *>(p));
+            const long long hi = __ldcg(reinterpret_cast<const long long *>(p) + 2);
+            c.index = lo.x;
+            c.asr_sim = __int_as_float(int(uint64_t(lo.y) & 0xFFFFFFFFull)); c.audio_sim = __int_as_float(int(uint64_t(lo.y) >> 32));
+            c.flags = uint32_t(uint64_t(hi) & 0xFFFFFFFFull); c.pad = 0u;
+            return c;
+        }, e.n_lists * k, qi, e, !finite, score, index, pos);
+        host_signal(e);
+        if (stamp) e.stamps[3] = globaltimer_ns();
+        return;
+    }
+    if (!e.out_index) return;          // candidates only (cab_search_candidates)
 
-    // ---- fused emit (single candidate list): rank the <= k candidates by counting ----------------
-    __syncthreads();
-    uint64_t *score = s_sort;                                        // reuse the selection buffer
-    const double wa = e.inline_weights ? e.w64_asr : e.w_asr[qi], wb = e.inline_weights ? e.w64_audio : e.w_audio[qi];
-    const int t = threadIdx.x;
-    if (t < a.k) score[t] = reference_fusion(s_cand[t], wa, wb, e.threshold);
-    __syncthreads();
-    const size_t o0 = size_t(qi) * e.k;
-    if (t < a.k) {
-        const uint64_t sc = score[t];
-        const int64_t gi = s_cand[t].index;
-        int rank = 0, n_res = 0;
-        for (int j = 0; j < a.k; ++j) {
-            const uint64_t sj = score[j];
-            n_res += sj != 0ull;
-            rank += (sj > sc) || (sj == sc && sj != 0ull && s_cand[j].index < gi);
-        }
-        if (sc != 0ull) {                                            // (score desc, index asc), :685
-            const cab_candidate c = s_cand[t];
-            e.out_index[o0 + rank] = c.index;
-            e.out_fusion[o0 + rank] = unorderable64(sc);
-            e.out_asr[o0 + rank] = c.asr_sim;
-            e.out_audio[o0 + rank] = c.audio_sim;
-            e.out_flags[o0 + rank] = uint8_t(c.flags);
-        }
-        if (t >= n_res) {                                            // pad beyond the results
-            e.out_index[o0 + t] = -1;
-            e.out_fusion[o0 + t] = 0.0;
-            e.out_asr[o0 + t] = 0.f;
-            e.out_audio[o0 + t] = 0.f;
-            e.out_flags[o0 + t] = 0;
-        }
-        if (t == 0) {
-            e.out_count[qi] = n_res;
-            if (qi == 0 && e.nonfinite_out) *e.nonfinite_out = *e.nonfinite;
-        }
-    }
+    // ---- fused emit (single candidate list) ------------------------------------------------------------
+    emit_ranked([&](int t) { return s_cand[t]; }, a.k, qi, e, !finite, score, index, pos);
     host_signal(e);
 }
 
@@ -379,118 +548,29 @@ void launch_finalize(const FinalizeArgs &a, const EmitArgs *fused_emit, cudaStre
     else cudaLaunchKernelEx(&cfg, finalize_kernel<CAB_F32>, a, e);
 }
 
-// ---- emit (merge of several candidate lists: sharded search) ---------------------------------------
-constexpr int kEmitThreads = 256;
-constexpr int kEmitMax = 1024;      // >= world(8) x CAB_MAX_K(128)
-
-__global__ void __launch_bounds__(kEmitThreads) emit_kernel(EmitArgs a) {
+// ---- emit as its own launch: merge of several candidate lists (cab_merge_candidates, and sharded
+// searches whose merge cannot ride in the finalize kernel) -----------------------------------------------
+__global__ void __launch_bounds__(kEmitMax) emit_kernel(EmitArgs a) {
     __shared__ uint64_t s_score[kEmitMax];     // orderable float64 fusion score, 0 = not a result
     __shared__ int64_t s_index[kEmitMax];
     __shared__ uint16_t s_pos[kEmitMax];
-    __shared__ int s_n;
 
     const int qi = blockIdx.x;
-    const int n_cand = a.n_lists * a.k;
-    int np2 = 64;
-    while (np2 < n_cand) np2 <<= 1;
     asm volatile("griddepcontrol.wait;" ::: "memory");      // programmatic dependent launch (see launch_emit)
-    const double wa = a.inline_weights ? a.w64_asr : a.w_asr[qi], wb = a.inline_weights ? a.w64_audio : a.w_audio[qi];
-    if (threadIdx.x == 0) s_n = 0;
-    if (a.wait_flags) {
-        // peer exchange: every rank's candidates of this epoch must have landed in our buffer
-        if (threadIdx.x < a.n_lists) {
-            const long long t0 = clock64();
-            while (ld_acquire_sys(a.wait_flags + threadIdx.x) != a.wait_epoch) {
-                if (clock64() - t0 > 20000000000ll) {          // ~10 s: a rank never arrived
-                    if (a.status) atomicExch(a.status, 7);
-                    __threadfence_system();
-                    asm volatile("trap;");
-                }
-            }
-        }
-        __syncthreads();
-    }
-    // candidate t of this query lives at list-major position:
-    auto cand_at = [&](int t) -> const cab_candidate * {
-        const int list = t / a.k, i = t - list * a.k;
-        return a.cands + (size_t(list) * a.n_queries + qi) * a.k + i;
-    };
-    for (int t = threadIdx.x; t < np2; t += kEmitThreads) {
-        uint64_t sc = 0ull;
-        int64_t gi = INT64_MAX;
-        if (t < n_cand) {
-            const cab_candidate c = *cand_at(t);
-            sc = reference_fusion(c, wa, wb, a.threshold);
-            if (sc) gi = c.index;
-        }
-        s_score[t] = sc; s_index[t] = gi; s_pos[t] = uint16_t(t);
-    }
-    if (n_cand <= kEmitThreads) {
-        // Few candidates (e.g. 8 shards x top-10): rank by counting instead of sorting -- no barriers.
-        __syncthreads();
-        const int t = threadIdx.x;
-        int rank = 0, n_res = 0;
-        const uint64_t sc = t < n_cand ? s_score[t] : 0ull;
-        const int64_t gi = t < n_cand ? s_index[t] : INT64_MAX;
-        for (int j = 0; j < n_cand; ++j) {
-            const uint64_t sj = s_score[j];
-            n_res += sj != 0ull;
-            rank += (sj > sc) || (sj == sc && sj != 0ull && s_index[j] < gi);
-        }
-        const size_t o0 = size_t(qi) * a.k;
-        if (sc != 0ull && rank < a.k) {
-            const cab_candidate c = *cand_at(t);
-            a.out_index[o0 + rank] = c.index;
-            a.out_fusion[o0 + rank] = unorderable64(sc);
-            a.out_asr[o0 + rank] = c.asr_sim;
-            a.out_audio[o0 + rank] = c.audio_sim;
-            a.out_flags[o0 + rank] = uint8_t(c.flags);
-        }
-        const int n_out = n_res < a.k ? n_res : a.k;
-        for (int i = n_out + t; i < a.k; i += kEmitThreads) {
-            a.out_index[o0 + i] = -1;
-            a.out_fusion[o0 + i] = 0.0;
-            a.out_asr[o0 + i] = 0.f;
-            a.out_audio[o0 + i] = 0.f;
-            a.out_flags[o0 + i] = 0;
-        }
-        if (t == 0) {
-            a.out_count[qi] = n_out;
-            if (qi == 0 && a.nonfinite_out) { *a.nonfinite_out = *a.nonfinite; }
-        }
-        host_signal(a);
-        return;
-    }
-    block_sort_results(s_score, s_index, s_pos, np2);
-    for (int i = threadIdx.x; i < a.k; i += kEmitThreads) {
-        const size_t o = size_t(qi) * a.k + i;
-        if (s_score[i] != 0ull) {
-            const cab_candidate c = *cand_at(s_pos[i]);
-            a.out_index[o] = c.index;
-            a.out_fusion[o] = unorderable64(s_score[i]);
-            a.out_asr[o] = c.asr_sim;
-            a.out_audio[o] = c.audio_sim;
-            a.out_flags[o] = uint8_t(c.flags);
-            atomicAdd(&s_n, 1);
-        } else {
-            a.out_index[o] = -1;
-            a.out_fusion[o] = 0.0;
-            a.out_asr[o] = 0.f;
-            a.out_audio[o] = 0.f;
-            a.out_flags[o] = 0;
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        a.out_count[qi] = s_n;
-        if (qi == 0 && a.nonfinite_out) { *a.nonfinite_out = *a.nonfinite; }
-    }
+    if (a.wait_flags) wait_peer_flags(a.wait_flags, a.n_lists, a.wait_epoch, a.status);
+    const int nq = a.n_queries, k = a.k;
+    const cab_candidate *lists = a.cands;
+    emit_ranked([&](int t) {
+        const int list = t / k, i = t - list * k;
+        return lists[(size_t(list) * nq + qi) * k + i];
+    }, a.n_lists * k, qi, a, false, s_score, s_index, s_pos);
     host_signal(a);
 }
 
 void launch_emit(const EmitArgs &a, cudaStream_t s) {
+    const int n_cand = a.n_lists * a.k;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(a.n_queries); cfg.blockDim = dim3(kEmitThreads); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cfg.gridDim = dim3(a.n_queries); cfg.blockDim = dim3(n_cand <= 256 ? 256 : kEmitMax); cfg.dynamicSmemBytes = 0; cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;

@@ -153,24 +153,32 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
 constexpr uint32_t kUmmaN = 2 * kTileRows;        // 256: [ASR | audio] x [leader | peer] halves
 constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(kUmmaN >> 3) << 17) | (uint32_t(256 >> 4) << 24);
 
-// ---- query preparation: normalise like sklearn normalize(X) and round to bf16, zero-pad to 256 -----
-__global__ void __launch_bounds__(256) prep_queries_kernel(const float *__restrict__ q_raw, int n_queries,
-                                                           __nv_bfloat16 *__restrict__ out, int *__restrict__ nonfinite) {
+// ---- per-pass prologue (one launch): normalise the queries like sklearn normalize(X), round to
+// bf16, zero-pad to 256 rows; clear the level histogram and the protocol status word --------------------
+__global__ void __launch_bounds__(256) gemm_prologue_kernel(const float *__restrict__ q_raw, int n_queries,
+                                                            __nv_bfloat16 *__restrict__ out, int32_t *__restrict__ levels,
+                                                            int *__restrict__ status) {
+    // programmatic dependent launch: the previous pass's finalize kernel has released the histogram
+    // (it consumed it before its launch_dependents); waiting for its completion here keeps the
+    // stream's completion order transitive for the kernels behind this one
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int lane = threadIdx.x & 31;
-    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = gtid >> 5;
+    for (int i = gtid; i < kGemmQueriesPerPass * kLevels; i += gridDim.x * blockDim.x) levels[i] = 0;
+    if (gtid == 0) *status = 0;
     if (row >= kGemmQueriesPerPass) return;
     float v[kDim / 32];
     float ss = 0.f;
-    bool bad = false;
 #pragma unroll
     for (int i = 0; i < kDim / 32; ++i) {
         v[i] = row < n_queries ? q_raw[size_t(row) * kDim + lane + 32 * i] : 0.f;
-        bad |= !isfinite(v[i]);
         ss = fmaf(v[i], v[i], ss);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(kFull, ss, o);
-    if (__any_sync(kFull, bad) || !isfinite(ss)) { if (lane == 0) *nonfinite = 1; }
+    // a NaN/Inf query becomes a NaN operand row: every score of it is NaN, nothing is selected,
+    // and the finalize kernel (which re-reads the raw query) reports it
     float norm = sqrtf(ss);
     if (norm == 0.f) norm = 1.f;
 #pragma unroll
@@ -232,6 +240,9 @@ gemm_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     cluster_sync();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    // Programmatic dependent launch: barrier init, TMEM allocation and the cluster handshake above
+    // overlapped the prologue kernel; its bf16 queries and the cleared histogram are read below.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     const int64_t n_tiles = (p.n_rows + kTileRows - 1) / kTileRows;
 
@@ -481,6 +492,10 @@ static size_t ws_counts_bytes(int sm_count) { return ((size_t(kGemmQueriesPerPas
 static size_t ws_queries_bytes() { return size_t(kGemmQueriesPerPass) * kDim * 2; }
 static size_t ws_levels_bytes() { return size_t(kGemmQueriesPerPass) * kLevels * 4; }
 size_t gemm_workspace_bytes(int, int, int sm_count) { return ws_counts_bytes(sm_count) + ws_queries_bytes() + ws_levels_bytes() + 256; }
+const int32_t *gemm_levels(const void *workspace, int sm_count) {
+    return reinterpret_cast<const int32_t *>(static_cast<const uint8_t *>(workspace) + ws_counts_bytes(sm_count) + ws_queries_bytes());
+}
+float gemm_level_step() { return kLevelStep; }
 
 void launch_gemm_scan(const ScanArgs &a, int sm_count, void *workspace, size_t workspace_bytes,
                       cudaStream_t s, std::string *err) {
@@ -493,25 +508,39 @@ void launch_gemm_scan(const ScanArgs &a, int sm_count, void *workspace, size_t w
     int32_t *levels = reinterpret_cast<int32_t *>(ws + ws_counts_bytes(sm_count) + ws_queries_bytes());
     int *status = reinterpret_cast<int *>(ws + ws_counts_bytes(sm_count) + ws_queries_bytes() + ws_levels_bytes());
 
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmSmemBytes));
-        if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return; }
-        attr_done = true;
+    {   // opt-in shared memory size: per kernel AND per device
+        static PerDeviceOnce once;
+        int dev = -1;
+        cudaGetDevice(&dev);
+        if (!once.done(dev)) {
+            cudaError_t e = cudaFuncSetAttribute(gemm_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmSmemBytes));
+            if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return; }
+            once.mark(dev);
+        }
     }
     CUtensorMap mq, ma, mb;
     if (!make_map(&mq, qb, kGemmQueriesPerPass, kQPerCta, err)) return;
     if (!make_map(&ma, a.asr, uint64_t(a.n_rows), kHalfRows, err)) return;
     if (!make_map(&mb, a.audio, uint64_t(a.n_rows), kHalfRows, err)) return;
 
-    cudaMemsetAsync(levels, 0, ws_levels_bytes() + sizeof(int), s);          // level histogram + status
-    prep_queries_kernel<<<kGemmQueriesPerPass / 8, 256, 0, s>>>(a.queries, a.n_queries, qb, a.nonfinite);
-
     GemmParams p{};
     p.flags = a.flags; p.n_rows = a.n_rows; p.wa32 = a.wa32; p.wb32 = a.wb32; p.n_queries = a.n_queries;
     p.k = a.k; p.select_threshold = a.select_threshold; p.lists = a.partial_keys; p.counts = counts;
     p.n_pairs = sm_count / 2; p.status = status; p.levels = levels;
-    gemm_scan_kernel<<<2 * p.n_pairs, kGemmThreads, kGemmSmemBytes, s>>>(mq, ma, mb, p);
+
+    // prologue -> scan, both with programmatic stream serialization: the prologue's launch overlaps
+    // the previous pass's finalize, the scan's setup (barriers, TMEM, cluster sync) the prologue.
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t c0{};
+    c0.gridDim = dim3(kGemmQueriesPerPass / 8); c0.blockDim = dim3(256); c0.dynamicSmemBytes = 0; c0.stream = s;
+    c0.attrs = attr; c0.numAttrs = 1;
+    cudaLaunchKernelEx(&c0, gemm_prologue_kernel, a.queries, a.n_queries, qb, levels, status);
+    cudaLaunchConfig_t c1{};
+    c1.gridDim = dim3(2 * p.n_pairs); c1.blockDim = dim3(kGemmThreads); c1.dynamicSmemBytes = kGemmSmemBytes; c1.stream = s;
+    c1.attrs = attr; c1.numAttrs = 1;
+    cudaLaunchKernelEx(&c1, gemm_scan_kernel, mq, ma, mb, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) *err = std::string("gemm_scan_kernel launch: ") + cudaGetErrorString(e);
 }

@@ -29,7 +29,7 @@ constexpr int kScanWarps = kScanThreads / 32;
 // the kernel remains HBM-bound at QT = 4).
 template <int DT, int U, int MB, int QT>
 __global__ void __launch_bounds__(kScanThreads, MB)
-gemv_scan_kernel(ScanArgs a) {
+cab_scan_kernel(ScanArgs a) {
     using TR = RowTraits<DT>;
     constexpr int G = TR::G, RW = TR::RW, CPR = TR::CPR;
     constexpr int kRowsPerIter = U * RW;
@@ -41,6 +41,11 @@ gemv_scan_kernel(ScanArgs a) {
     uint64_t(*s_keys)[QT][kWarpCap] = reinterpret_cast<uint64_t(*)[QT][kWarpCap]>(scan_smem);
     int(*s_count)[QT] = reinterpret_cast<int(*)[QT]>(scan_smem + sizeof(uint64_t) * kScanWarps * QT * kWarpCap);
     float *s_q = reinterpret_cast<float *>(scan_smem + sizeof(uint64_t) * kScanWarps * QT * kWarpCap + sizeof(int) * kScanWarps * QT);
+    // Programmatic dependent launch (see ScanArgs::wait_early): a query / weights in device memory
+    // may have been written by the kernel right in front of this one on the caller's stream (the
+    // MiniLM layer that produced the embedding), so nothing is read from global memory before it
+    // has completed.
+    if (a.wait_early) asm volatile("griddepcontrol.wait;" ::: "memory");
     if (a.inl.use_query) {
         // Kernel-argument query -> shared memory once per CTA (per-lane indexed reads of the
         // constant bank serialise 32-way; done by every warp they cost ~10 us per scan).
@@ -55,14 +60,13 @@ gemv_scan_kernel(ScanArgs a) {
     float q[QT][TR::NQ];
     ScanWeights w[QT];
     WarpTopK top[QT];
-    bool all_finite = true;
 #pragma unroll
     for (int t = 0; t < QT; ++t) {
         const bool valid = q0 + t < a.n_queries;
         const int qi = valid ? q0 + t : q0;       // pad the group with its first query, never pushed
         const float *qsrc = a.queries + size_t(qi) * kDim;
-        bool ok = load_query<DT>([&](int i) { return a.inl.use_query ? s_q[i] : qsrc[i]; }, lane, q[t]);
-        all_finite &= ok;
+        // a NaN/Inf query scores NaN everywhere and selects nothing; the finalize kernel reports it
+        load_query<DT>([&](int i) { return a.inl.use_query ? s_q[i] : qsrc[i]; }, lane, q[t]);
         w[t] = a.inl.use_weights ? ScanWeights{a.inl.wa32, a.inl.wb32} : ScanWeights{a.wa32[qi], a.wb32[qi]};
         top[t].init(s_keys[warp][t], a.k, valid ? bound_key(a.select_threshold) : ~0ull);
     }
@@ -98,11 +102,8 @@ gemv_scan_kernel(ScanArgs a) {
     const int64_t n_chunks = n_big + n_small;
     unsigned int *counter = a.work_counters + blockIdx.y;
     int64_t chunk = gwarp;
-    // Programmatic dependent launch: everything above (query staging + normalisation) may overlap
-    // the previous search's finalize kernel; the ticket counter (reset by that kernel) and the
-    // partial-key slots (read by it) are only touched after this wait.
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (!all_finite && lane == 0) *a.nonfinite = 1;           // NaN/Inf query: sklearn raises ValueError
+    // The ticket counter was reset by the previous search's finalize kernel before it released its
+    // dependents (griddepcontrol.launch_dependents), i.e. before this grid could start.
     unsigned int ticket = 0;                                  // lane 0: result of the in-flight atomic
     if (chunk < n_chunks && lane == 0) ticket = atomicAdd(counter, 1u);
 
@@ -167,6 +168,12 @@ gemv_scan_kernel(ScanArgs a) {
         }
     }
 
+    // The partial-key slots written below were read by the previous search's finalize kernel before
+    // it released its dependents; waiting here for that kernel to have COMPLETED (it has, long ago:
+    // the scan took hundreds of microseconds) keeps the stream's completion order transitive -- the
+    // finalize kernel after this scan waits on this grid only.
+    if (!a.wait_early) asm volatile("griddepcontrol.wait;" ::: "memory");
+
     // ---- this warp's best k per query, then the CTA's best k --------------------------------------
 #pragma unroll
     for (int t = 0; t < QT; ++t) {
@@ -224,10 +231,13 @@ int gemv_max_grid(int sm_count) { return sm_count * 4; }
 template <int DT, int U, int MB, int QT>
 static void launch_one(const ScanArgs &a, dim3 grid, cudaStream_t s) {
     constexpr size_t smem = sizeof(uint64_t) * kScanWarps * QT * kWarpCap + sizeof(int) * kScanWarps * QT + sizeof(float) * kDim;
-    static bool attr_done = false;
-    if (smem > 48 * 1024 && !attr_done) {
-        cudaFuncSetAttribute(gemv_scan_kernel<DT, U, MB, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        attr_done = true;
+    if (smem > 48 * 1024) {                       // opt-in shared memory size: per kernel AND per device
+        static PerDeviceOnce once;
+        int dev = -1;
+        cudaGetDevice(&dev);
+        if (!once.done(dev) &&
+            cudaFuncSetAttribute(cab_scan_kernel<DT, U, MB, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) == cudaSuccess)
+            once.mark(dev);
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.blockDim = dim3(kScanThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
@@ -235,7 +245,7 @@ static void launch_one(const ScanArgs &a, dim3 grid, cudaStream_t s) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, gemv_scan_kernel<DT, U, MB, QT>, a);
+    cudaLaunchKernelEx(&cfg, cab_scan_kernel<DT, U, MB, QT>, a);
 }
 
 template <int DT>

@@ -3,9 +3,20 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/cab.h"
 
 namespace cab {
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a property of (kernel, DEVICE): one of these
+// per kernel remembers on which device ordinals it has been set (a process may hold indices on
+// several GPUs, cab.h "Conventions").  Thread-safe; ordinals >= 64 simply set it on every launch.
+struct PerDeviceOnce {
+    std::atomic<uint64_t> mask{0};
+    bool done(int dev) const { return dev >= 0 && dev < 64 && ((mask.load(std::memory_order_acquire) >> dev) & 1ull); }
+    void mark(int dev) { if (dev >= 0 && dev < 64) mask.fetch_or(1ull << dev, std::memory_order_release); }
+};
 
 // ---- ingest (cab_ingest.cu) --------------------------------------------------------------------
 // Normalise n raw fp32 rows (sklearn `normalize` semantics) into the store at row offset `dst_row`.
@@ -55,9 +66,16 @@ struct ScanArgs {
                                // [n_queries][n_partials][kGemmListCap] (GEMM, with counts)
     int32_t *partial_counts;   // GEMM only: [n_queries][n_partials]
     int n_partials;            // == grid size of the scan (GEMV) / number of CTA pairs (GEMM)
-    int *nonfinite;            // set if a query holds NaN/Inf
     unsigned int *work_counters;   // GEMV: [n_queries] chunk tickets, zero on entry (finalize resets them)
     int chunk_rows;                // GEMV: rows per dynamically scheduled chunk
+    // Where the scan executes griddepcontrol.wait (it is launched with programmatic stream
+    // serialization).  1: before its first global read -- the device query / staged weights may have
+    // been written by the kernel right in front of it on the caller's stream.  0: only before it
+    // publishes its partial lists: everything it touches earlier (ticket counters, its own shared
+    // memory) was released by the preceding finalize kernel BEFORE that kernel's
+    // griddepcontrol.launch_dependents, so the scan of search i+1 streams the corpus while search
+    // i's finalize / exchange / merge is still in flight.
+    int wait_early;
     InlineParams inl;
 };
 struct GemvConfig {
@@ -132,6 +150,12 @@ struct FinalizeArgs {
     cab_candidate *cands;      // out [n_queries][k], best-first by scan score, index -1 = empty
     int force_general;         // test hook: skip the head-bound fast path
     unsigned int *work_counters;   // [n_queries] reset to 0 for the next scan (may be null)
+    // tensor-core scan only: the per-query score-level histogram it left behind ([n_queries][64],
+    // level j = fused score in [select_threshold + j*step, +step)); gives the finalize a bound that
+    // at most (k + one level's population) keys exceed, so they are ranked by counting, not sorted
+    const int32_t *levels;
+    float select_threshold;
+    float level_step;
     PeerPush peer;
     InlineParams inl;
 };
@@ -155,8 +179,9 @@ struct EmitArgs {
     float *out_audio;
     uint8_t *out_flags;
     int32_t *out_count;
-    const int *nonfinite;         // device flag set by scan / ingest kernels
-    int *nonfinite_out;           // copy of it next to the outputs (may be null)
+    // A NaN/Inf query (sklearn raises ValueError for the reference) has no results: out_count = -1,
+    // and *nonfinite_out (host-visible block, zeroed by the host before the launch) is set to 1.
+    int *nonfinite_out;           // may be null (device outputs: out_count = -1 is the signal)
     // zero-copy host results: outputs point into mapped pinned host memory; when every CTA of the
     // (last) launch has written, done_flag (also in that block) is set to done_epoch for the host
     uint32_t *done_flag;          // null = outputs are ordinary device memory
@@ -166,7 +191,13 @@ struct EmitArgs {
     const uint32_t *wait_flags;   // null = no wait
     uint32_t wait_epoch;
     int *status;                  // set to 7 (and the kernel traps) if the wait times out
+    // sharded search, diagnostic: %globaltimer (ns) at {scan complete, own flag raised, all flags
+    // seen, results written} of query 0's CTA; null = not recorded
+    unsigned long long *stamps;
 };
+// cab_candidate.index of every slot of a query that holds NaN/Inf (travels through the exchange so
+// that a merge without the query -- cab_merge_candidates -- reports it too)
+constexpr int64_t kBadQueryIndex = -2;
 // Push a local candidate block [n_queries x k] to every peer and raise the flags (used when there
 // was nothing to scan; otherwise the finalize kernel pushes).
 void launch_peer_push(const cab_candidate *local, int n_queries, int k, const PeerPush &peer, cudaStream_t s);

@@ -88,11 +88,12 @@ class _DeviceLibrary:
             self._last_seg, self._table_generation = table, table.generation
             table.bind_index(self.index)
         if table.n_pending:
-            row0, asr, audio, flags = table.drain_pending()
+            row0, asr, audio, flags = table.pending_arrays()
             if row0 != len(self.index):
                 raise RuntimeError(f"segment table and device index are out of step "
                                    f"(table rows before the new ones: {row0}, index rows: {len(self.index)})")
-            self.index.append(asr, audio, flags)                      # ValueError on NaN/Inf
+            self.index.append(asr, audio, flags)                      # ValueError on NaN/Inf: nothing appended,
+            table.commit_pending(asr.shape[0])                        # nothing forgotten -- the next search retries
         if len(self.index) != len(table):
             raise RuntimeError(f"segment table has {len(table)} rows, the device index {len(self.index)}")
         self.n_synced = len(table)

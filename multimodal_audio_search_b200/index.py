@@ -127,6 +127,13 @@ class SegmentIndex:
     def last_scan_ms(self) -> float:
         return float(self._lib.cab_index_last_scan_ms(self._h))
 
+    def exchange_stamps(self, max_rows: int = 64) -> np.ndarray:
+        """Option "stamp_exchange": uint64 [n, 4] %globaltimer ns of the last sharded searches --
+        {scan complete, own flag raised, all ranks' flags seen, results written} (oldest first)."""
+        out = np.zeros((max_rows, 4), dtype=np.uint64)
+        n = int(self._lib.cab_index_exchange_stamps(self._h, _ptr(out), int(max_rows)))
+        return out[:n]
+
     def _stream(self):
         """torch's current stream for the C-ABI.  NULL means "the handle's own stream" there, and
         torch's default stream IS the NULL handle, so it is passed as cudaStreamLegacy (0x1)."""

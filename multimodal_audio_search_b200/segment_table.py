@@ -269,10 +269,12 @@ class SegmentTable(Sequence):
     def n_pending(self) -> int:
         return len(self._pending)
 
-    def drain_pending(self):
-        """Embeddings + flags of the rows appended since the last drain, as the arrays
-        `SegmentIndex.append` takes (None embedding -> zero row, :640-641); the table forgets
-        them (they live in HBM from here on).  Returns (first_row, asr, audio, flags)."""
+    def pending_arrays(self):
+        """Embeddings + flags of the rows appended since the last commit, as the arrays
+        `SegmentIndex.append` takes (None embedding -> zero row, :640-641).  Nothing is forgotten
+        yet: call `commit_pending(m)` once the device index has accepted them, so a failed append
+        (NaN row -> ValueError, out of memory) leaves table and index in step and can be retried.
+        Returns (first_row, asr, audio, flags)."""
         m = len(self._pending)
         row0 = self._pending_row0
         asr = np.zeros((m, DIM), dtype=np.float32)
@@ -284,9 +286,18 @@ class SegmentTable(Sequence):
                 audio[i] = _embedding_row(b)
         flags = (self.column("asr_success", row0, row0 + m).astype(np.uint8)
                  | (self.column("audio_success", row0, row0 + m).astype(np.uint8) << 1))
-        self._pending = []
-        self._pending_row0 = row0 + m
         return row0, asr, audio, flags
+
+    def commit_pending(self, m: int) -> None:
+        """Forget the host copies of the first `m` pending rows: they live in HBM from here on."""
+        del self._pending[:m]
+        self._pending_row0 += m
+
+    def drain_pending(self):
+        """`pending_arrays()` + `commit_pending()` in one step (callers that cannot fail)."""
+        out = self.pending_arrays()
+        self.commit_pending(out[1].shape[0])
+        return out
 
     # ---- row access ---------------------------------------------------------------------------
     def _num_at(self, name: str, i: int):

@@ -1,0 +1,274 @@
+"""GPU tests added in round 2: stream/launch ordering of the search kernels (programmatic dependent
+launch), non-finite queries with device outputs, indices on several devices in one process, and
+the NVLink peer-memory exchange protocol (fused push + flag + merge in the finalize kernel)
+exercised by TWO PROCESSES sharing one GPU, so it runs on the driver's single-GPU box too.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from multimodal_audio_search_b200 import SegmentIndex, synth          # noqa: E402
+from oracle import numpy_oracle as no                                 # noqa: E402  (checker only)
+from tests.util import BF16_TOL, FP32_TOL, assert_topk_matches, result_row   # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib(seed, n, nq, plants, dtype="fp32", partial=False):
+    idx = SegmentIndex(dtype, capacity=n)
+    idx.append_synth(seed, n, 0, n, n_queries=nq, plants=plants, partial=partial)
+    return idx
+
+
+def test_query_written_by_the_kernel_in_front_of_a_single_query_search():
+    """the scan is launched with programmatic stream serialization; a 1-query search
+    with a DEVICE query has no staging copy in front of it, so the kernel in front of the scan is
+    the caller's own producer (MiniLM's last layer in the app).  The scan must not read the query
+    before that kernel has completed."""
+    torch = pytest.importorskip("torch")
+    seed, n, nq = 91, 400_000, 24
+    idx = _lib(seed, n, nq, 30)
+    q = synth.raw_queries(seed, 0, nq)
+    want = [idx.search(q[i:i + 1], 0.5, 0.5, k=10) for i in range(nq)]
+    qd = torch.from_numpy(q).cuda()
+    buf = torch.zeros(384, device="cuda")
+    big = torch.randn(64 << 20, device="cuda")              # producer: a long kernel, then the query write
+    got = []
+    for i in range(nq):
+        # a slow elementwise kernel followed by the (tiny) kernel that writes the query; the search
+        # goes out right behind them on the same stream
+        big.mul_(1.0000001)
+        buf.copy_(qd[i] + big[:384] * 0.0)
+        got.append(idx.search(buf.unsqueeze(0), 0.5, 0.5, k=10))
+    torch.cuda.synchronize()
+    for i in range(nq):
+        np.testing.assert_array_equal(got[i].indices.cpu().numpy(), want[i].indices)
+        np.testing.assert_array_equal(got[i].fusion.cpu().numpy(), want[i].fusion)
+    idx.close()
+
+
+@pytest.mark.parametrize("dtype,path,nq", [("fp32", "gemv", 1), ("fp32", "gemv", 5), ("bf16", "gemm", 70)])
+def test_nonfinite_query_with_device_outputs_is_reported_per_query_and_leaves_no_residue(dtype, path, nq):
+    """with out_loc = CAB_DEVICE nobody read the non-finite flag; it stayed set and
+    broke the next append / host search.  Now: out_count = -1 for exactly the bad queries, nothing
+    sticky on the handle."""
+    torch = pytest.importorskip("torch")
+    seed, n = 17, 30_000
+    idx = _lib(seed, n, nq, 24, dtype)
+    q = synth.raw_queries(seed, 0, nq)
+    bad = q.copy()
+    bad_rows = sorted({0, nq // 2})
+    for r in bad_rows:
+        bad[r, 7] = np.nan if r == 0 else np.inf
+    good = idx.search(q, 0.5, 0.5, k=10, path=path)
+    dev = idx.search(torch.from_numpy(bad).cuda(), 0.5, 0.5, k=10, path=path)
+    cnt = dev.count.cpu().numpy()
+    ind = dev.indices.cpu().numpy()
+    for r in range(nq):
+        if r in bad_rows:
+            assert cnt[r] == -1 and (ind[r] == -1).all()
+        else:
+            assert cnt[r] == good.count[r]
+            np.testing.assert_array_equal(ind[r], good.indices[r])
+    # no residue: a valid append and a valid host search right after
+    a, b, f, _ = synth.library(seed + 1, 64, 1, 4)
+    idx.append(a, b, f)
+    again = idx.search(q, 0.5, 0.5, k=10, path=path)
+    assert (again.count >= good.count).all()
+    # host outputs: the reference's ValueError (sklearn's message)
+    with pytest.raises(ValueError, match="NaN|infinity"):
+        idx.search(bad, 0.5, 0.5, k=10, path=path)
+    ok = idx.search(q, 0.5, 0.5, k=10, path=path)
+    np.testing.assert_array_equal(ok.indices, again.indices)
+    # the same through candidates + merge (the merge has no query: the marker rides in the records)
+    cands = idx.search_candidates(bad, 0.5, 0.5, k=10, path=path)
+    merged = idx.merge_candidates(cands.unsqueeze(0), 0.5, 0.5, k=10, to_host=False)
+    mc = merged.count.cpu().numpy()
+    assert [int(mc[r]) == -1 for r in range(nq)] == [r in bad_rows for r in range(nq)]
+    with pytest.raises(ValueError):
+        idx.merge_candidates(cands.unsqueeze(0), 0.5, 0.5, k=10, to_host=True)
+    idx.close()
+
+
+def test_indices_on_two_devices_in_one_process():
+    """cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: the 64 KB multi-query scan and
+    the 214 KB tensor-core scan must launch on a second device of the same process."""
+    torch = pytest.importorskip("torch")
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two visible GPUs")
+    seed, n, nq = 5, 60_000, 70
+    q = synth.raw_queries(seed, 0, nq)
+    out = []
+    for dev in (0, 1):
+        idx = SegmentIndex("bf16", capacity=n, device=dev)
+        idx.append_synth(seed, n, 0, n, n_queries=nq, plants=24)
+        out.append((idx.search(q[:8], 0.4, 0.6, k=10, path="gemv"), idx.search(q, 0.4, 0.6, k=10, path="gemm")))
+        idx.close()
+    for a, b in zip(out[0], out[1]):
+        np.testing.assert_array_equal(a.indices, b.indices)
+        np.testing.assert_array_equal(a.fusion, b.fusion)
+
+
+def test_failed_append_leaves_table_and_index_in_step():
+    """the columnar table used to forget a batch's embeddings before the device append
+    had succeeded."""
+    from multimodal_audio_search_b200 import DualPipelineAudioSearch
+    from multimodal_audio_search_b200.segment_table import SegmentTable
+
+    class Emb:
+        def encode(self, text):
+            return synth.raw_queries(3, 0, 1)[0]
+
+    a, b, f, _ = synth.library(3, 50, 1, 10)
+
+    def seg(i, bad=False):
+        e = a[i].copy()
+        if bad:
+            e[3] = np.nan
+        return {"segment_id": f"seg_{i}", "start_time": 10.0 * i, "end_time": 10.0 * i + 10, "duration": 10.0,
+                "asr_text": "t", "asr_embedding": e, "asr_success": True, "audio_description": "d",
+                "audio_embedding": b[i], "audio_success": True, "audio_data": np.zeros(4, np.float32),
+                "sample_rate": 16000}
+    eng = DualPipelineAudioSearch(text_embedder=Emb())
+    eng.audio_segments = SegmentTable.from_segments([seg(i) for i in range(20)])
+    r0, _ = eng.search_with_fusion("anything")
+    eng.audio_segments.extend([seg(i, bad=(i == 25)) for i in range(20, 30)])
+    with pytest.raises(ValueError):
+        eng.search_with_fusion("anything")
+    with pytest.raises(ValueError):                     # still the reference's error, not "out of step"
+        eng.search_with_fusion("anything")
+    assert eng.audio_segments.n_pending == 10           # nothing was forgotten
+    assert len(eng._cab_library.index) == 20
+
+
+def test_pipelined_searches_match_one_at_a_time():
+    """Option "queries_settled": search i+1's scan starts while search i's finalize is in flight.
+    A long run of back-to-back device searches (GEMV single, GEMV batch, tensor-core) must equal
+    the same searches issued one at a time with a synchronisation in between."""
+    torch = pytest.importorskip("torch")
+    seed, n, nq = 23, 300_000, 96
+    for dtype in ("fp32", "bf16"):
+        idx = _lib(seed, n, nq, 30, dtype, partial=True)
+        q = synth.raw_queries(seed, 0, nq)
+        qd = torch.from_numpy(q).cuda()
+        wa = np.linspace(0.2, 0.8, nq); wb = 1 - wa
+        plan = [(i, i + 1, "gemv") for i in range(40)] + [(40, 47, "gemv"), (0, 33, "gemv")]
+        if dtype == "bf16":
+            plan += [(0, 96, "gemm"), (3, 4, "gemv"), (10, 80, "gemm")]
+        want = []
+        for lo, hi, path in plan:
+            want.append(idx.search(qd[lo:hi], wa[lo:hi], wb[lo:hi], k=10, path=path))
+            torch.cuda.synchronize()
+        idx.set_option("queries_settled", 1)
+        for rep in range(3):
+            got = [idx.search(qd[lo:hi], wa[lo:hi], wb[lo:hi], k=10, path=path) for lo, hi, path in plan]
+            torch.cuda.synchronize()
+            for g, w in zip(got, want):
+                assert torch.equal(g.indices, w.indices) and torch.equal(g.fusion, w.fusion) and torch.equal(g.count, w.count)
+        idx.close()
+
+
+def test_fused_exchange_world_of_one_equals_plain_search():
+    """cab_search_sharded with a world of one rank: the finalize kernel pushes into its own exchange
+    buffer, raises and waits on its own flag and merges -- same answer as cab_search, over many
+    epochs (both buffer parities), host and device outputs, k = 10 and 100."""
+    torch = pytest.importorskip("torch")
+    seed, n, nq = 29, 120_000, 40
+    for dtype in ("fp32", "bf16"):
+        idx = _lib(seed, n, nq, 220, dtype, partial=True)
+        idx.row_base = 1000
+        idx.peer_attach(idx.peer_init(0, 1, max_queries=128, max_k=128))
+        idx.set_option("stamp_exchange", 1)
+        q = synth.raw_queries(seed, 0, nq)
+        qd = torch.from_numpy(q).cuda()
+        for k in (10, 100):
+            for lo, hi in ((0, 1), (1, 2), (2, 9), (0, 40)):
+                wa = np.linspace(0.3, 0.7, hi - lo); wb = 1 - wa
+                ref = idx.search(q[lo:hi], wa, wb, k=k)
+                host = idx.search_sharded(q[lo:hi], wa, wb, k=k)
+                dev = idx.search_sharded(qd[lo:hi], wa, wb, k=k, to_host=False)
+                np.testing.assert_array_equal(host.indices, ref.indices)
+                np.testing.assert_array_equal(host.fusion, ref.fusion)
+                np.testing.assert_array_equal(host.count, ref.count)
+                np.testing.assert_array_equal(dev.indices.cpu().numpy(), ref.indices)
+                np.testing.assert_array_equal(dev.asr_sim.cpu().numpy(), ref.asr_sim)
+        st = idx.exchange_stamps()
+        assert len(st) > 0 and (np.diff(st.astype(np.int64), axis=1) >= 0).all()
+        idx.close()
+
+
+# ---- two processes, one GPU: the peer-memory exchange end to end -----------------------------------------
+def _peer_worker(rank, world, port, seed, n, nq, out_path):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from multimodal_audio_search_b200 import SegmentIndex, ShardedSearcher, synth
+    from multimodal_audio_search_b200.sharded import shard_range
+    torch.cuda.set_device(0)
+    lo, hi = shard_range(n, rank, world)
+    idx = SegmentIndex("fp32", capacity=hi - lo, device=0)
+    idx.append_synth(seed, n, lo, hi, n_queries=nq, plants=60, partial=True)
+    idx.row_base = lo
+    sh = ShardedSearcher(idx, rank, world, exchange="p2p", max_queries=128, max_k=128)
+    q = synth.raw_queries(seed, 0, nq)
+    qd = torch.from_numpy(q).cuda()
+    wa = np.linspace(0.2, 0.8, nq); wb = 1 - wa
+    res = {}
+    # fused merge (few queries, one pass), separate merge launch (many queries), both buffer parities,
+    # host and device outputs, k = 10 / 100
+    cases = [(0, 1, 10, True), (1, 2, 10, False), (2, 3, 100, True), (3, 12, 10, False), (0, 48, 10, True),
+             (0, 100, 10, False), (5, 6, 100, False)]
+    for rep in range(2):
+        for ci, (a, b, k, to_host) in enumerate(cases):
+            r = sh.search(q[a:b] if to_host else qd[a:b], wa[a:b], wb[a:b], k=k, to_host=to_host)
+            ind = r.indices if to_host else r.indices.cpu().numpy()
+            fus = r.fusion if to_host else r.fusion.cpu().numpy()
+            cnt = r.count if to_host else r.count.cpu().numpy()
+            res[f"i{rep}_{ci}"], res[f"f{rep}_{ci}"], res[f"c{rep}_{ci}"] = ind, fus, cnt
+    torch.cuda.synchronize()
+    dist.barrier()
+    np.savez(out_path + f".{rank}.npz", **res)
+    idx.close()
+    dist.destroy_process_group()
+
+
+def test_peer_exchange_two_processes_one_gpu(tmp_path):
+    """World of 2 ranks = 2 processes, both on cuda:0, exchange buffers shared through CUDA IPC: the
+    finalize kernel's peer stores + epoch flags + merge must give every rank exactly the answer of
+    one index over the whole library.  (The GPU time-slices the two contexts; the flag waits are
+    bounded, so a protocol bug fails the test instead of hanging the box.)"""
+    torch = pytest.importorskip("torch")
+    import torch.multiprocessing as mp
+    seed, n, nq, world = 41, 90_000, 100, 2
+    whole = SegmentIndex("fp32", capacity=n)
+    whole.append_synth(seed, n, 0, n, n_queries=nq, plants=60, partial=True)
+    q = synth.raw_queries(seed, 0, nq)
+    wa = np.linspace(0.2, 0.8, nq); wb = 1 - wa
+    cases = [(0, 1, 10), (1, 2, 10), (2, 3, 100), (3, 12, 10), (0, 48, 10), (0, 100, 10), (5, 6, 100)]
+    want = [whole.search(q[a:b], wa[a:b], wb[a:b], k=k) for a, b, k in cases]
+    whole.close()
+    out = str(tmp_path / "peer")
+    port = 29500 + (os.getpid() % 2000)
+    ctx = mp.spawn(_peer_worker, args=(world, port, seed, n, nq, out), nprocs=world, join=False)
+    deadline = 240
+    import time
+    t0 = time.time()
+    while not ctx.join(timeout=5):
+        if time.time() - t0 > deadline:
+            for p in ctx.processes:
+                p.kill()
+            pytest.fail("peer exchange workers did not finish")
+    for rank in range(world):
+        z = np.load(out + f".{rank}.npz")
+        for rep in range(2):
+            for ci, w in enumerate(want):
+                np.testing.assert_array_equal(z[f"i{rep}_{ci}"], w.indices, err_msg=f"rank {rank} case {ci}")
+                np.testing.assert_array_equal(z[f"f{rep}_{ci}"], w.fusion)
+                np.testing.assert_array_equal(z[f"c{rep}_{ci}"], w.count)
