@@ -4,14 +4,30 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     torchrun --nproc-per-node N bench.py --gpus N ...          (driver, N > 1)
 
-A "step" is ONE query over the whole (sharded) library: scan both corpora, fuse, top-k.
-Default workload = BASELINE.json configs[1]: 1M-segment dual corpus per GPU, single query, fp32
+A "step" is ONE pass of the hot path over one batch of queries: scan both corpora, fuse, top-k.
+Headline workload = BASELINE.json configs[1]: 1M-segment dual corpus per GPU, single query, fp32
 GEMV + fusion + top-10.  With N GPUs the library is N x 1M segments sharded by segment (weak
-scaling); every step each rank scans its shard, the per-shard top-k candidate blocks are
-all-gathered (NCCL) and merged on every rank.
+scaling); every step each rank scans its shard, stores its top-k into every rank's exchange buffer
+over NVLink peer memory and merges -- all inside the kernels of the step.
 
-Prints ONE JSON line (rank 0).  `value` is queries/s normalised to 1M-segment libraries, i.e.
-queries/s x (global segments / 1M): at N=1 it is plain queries/s on the 1M config.
+What the one JSON line (rank 0) carries:
+  value / ms_per_step   device-resident throughput: the K-step region (barrier + synchronize on both
+                        sides, CUDA events, max over ranks) is repeated `--reps` times; the MEDIAN
+                        repetition is reported, min / max beside it ("repetitions")
+  e2e                   the same through the host API: host query in, host results out, per step
+  e2e_dropin            the same through the reference-facing call search_with_fusion(str) on a
+                        1M-row library (weight analysis + embedder hand-off + result dicts)
+  roofline              scan kernel timed with CUDA events on its stream
+  parity_check          the results the timed loops produced, checked against the oracle
+                        (every returned row + every planted neighbour regenerated on the host);
+                        N > 1: also the sharded answer against ONE index holding all rows
+  secondary             the other BASELINE configs measured in the same process
+                        (N = 1: 10M fp32 single query, 10M bf16 x 256 queries on tensor cores,
+                        the pruning worst cases; N > 1: 12.5M bf16 per GPU = 100M over 8)
+  cpu_baseline          the oracle port on the host cores (N = 1)
+
+`value` is queries/s normalised to 1M-segment libraries, i.e. queries/s x (global segments / 1M):
+at N = 1 it is plain queries/s on the 1M config.
 """
 from __future__ import annotations
 
@@ -29,22 +45,40 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SEED = 20261018
+METRIC = "fused dual-corpus 384D top-k queries/s"
+UNIT = "queries/s (per 1M segments)"
 WORKLOADS = {
-    # name: (segments per GPU, dtype, queries per step, k, path)
-    "1m_fp32_q1_top10": (1_000_000, "fp32", 1, 10, "gemv"),
-    "10m_fp32_q1_top10": (10_000_000, "fp32", 1, 10, "gemv"),
-    "10m_bf16_q1_top10": (10_000_000, "bf16", 1, 10, "gemv"),
-    "10m_bf16_q256_top100": (10_000_000, "bf16", 256, 100, "gemm"),
-    "12m5_bf16_q1_top100": (12_500_000, "bf16", 1, 100, "gemv"),     # 100M over 8 GPUs
+    # name: (segments per GPU, dtype, queries per step, k, path, distribution)
+    "1m_fp32_q1_top10": (1_000_000, "fp32", 1, 10, "gemv", "planted"),
+    "10m_fp32_q1_top10": (10_000_000, "fp32", 1, 10, "gemv", "planted"),
+    "10m_bf16_q1_top10": (10_000_000, "bf16", 1, 10, "gemv", "planted"),
+    "10m_bf16_q256_top100": (10_000_000, "bf16", 256, 100, "gemm", "planted"),
+    "12m5_bf16_q1_top100": (12_500_000, "bf16", 1, 100, "gemv", "planted"),     # 100M over 8 GPUs
+    # pruning worst cases: every row beats the running k-th best /
+    # many rows above the threshold
+    "10m_fp32_q1_top10_ascending": (10_000_000, "fp32", 1, 10, "gemv", "ascending"),
+    "10m_fp32_q1_top10_clustered": (10_000_000, "fp32", 1, 10, "gemv", "clustered"),
+    "10m_bf16_q256_top100_ascending": (10_000_000, "bf16", 256, 100, "gemm", "ascending"),
+    "10m_bf16_q256_top100_clustered": (10_000_000, "bf16", 256, 100, "gemm", "clustered"),
 }
+SECONDARY = {1: ["10m_fp32_q1_top10", "10m_bf16_q256_top100"], "multi": ["12m5_bf16_q1_top100"]}
+W_CLASSES = [0.5, 0.2, 0.3, 0.4, 0.6, 0.7, 0.8]       # the achievable w_asr classes (audio_search.py:593-620)
 
 
 def bytes_per_row(dtype):           # 2 corpora x 384 x sizeof(elem)
     return 2 * 384 * (4 if dtype == "fp32" else 2)
 
 
+def workload_config(name, world, threshold):
+    n_rows, dtype, nq, k, path, dist_kind = WORKLOADS[name]
+    return {"workload": name, "segments_per_gpu": n_rows, "global_segments": n_rows * world,
+            "queries_per_step": nq, "k": k, "path": path, "threshold": threshold, "distribution": dist_kind,
+            "l2": "inputs larger than L2 (corpus bytes per GPU >> 126 MB)",
+            "value_definition": "queries/s x global_segments/1e6"}
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled while the timed regions run."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -55,7 +89,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -63,20 +97,17 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
+    def mark(self):
+        return time.perf_counter()
+
+    def window(self, t0, t1):
+        """Clock record of the samples taken in [t0, t1] (all samples if the window caught none)."""
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows]
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             if len(r) < 9:
                 continue
             try:
@@ -86,8 +117,19 @@ class ClockSampler:
             for name, v in zip(names, r[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvidia-smi unavailable"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "samples": len(sm), "reasons": sorted(reasons)}
+
+    def stop(self):
+        if not self.proc:
+            return
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
 
 
 def peaks():
@@ -100,17 +142,29 @@ def peaks():
     return 6650.0, 1590.0, 1400.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_baseline(n_rows, dtype, k, max_seconds=25.0):
-    """The oracle port (numpy, all host cores through OpenBLAS) on the same workload shape.
-    Isotropic random rows (cheap to generate) -- the arithmetic per segment is identical."""
-    from oracle import numpy_oracle as no
+def host_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return int(max([i.get("num_threads", 1) for i in threadpool_info()] or [1]))
+    except Exception:
+        return os.cpu_count()
+
+
+def cpu_sample(n_rows):
+    """Isotropic unit rows (cheap to generate; the arithmetic per segment is what is timed)."""
     rng = np.random.default_rng(1)
     sample = min(n_rows, 1_000_000)
     a = rng.standard_normal((sample, 384), dtype=np.float32)
     b = rng.standard_normal((sample, 384), dtype=np.float32)
     a /= np.linalg.norm(a, axis=1, keepdims=True)
     b /= np.linalg.norm(b, axis=1, keepdims=True)
-    f = np.full(sample, 3, np.uint8)
+    return sample, a, b, np.full(sample, 3, np.uint8), rng
+
+
+def cpu_baseline(n_rows, dtype, k, max_seconds=20.0):
+    """The oracle port (numpy, all host cores through OpenBLAS) on the same workload shape."""
+    from oracle import numpy_oracle as no
+    sample, a, b, f, rng = cpu_sample(n_rows)
     q = rng.standard_normal(384).astype(np.float32)
     q /= np.linalg.norm(q)
     no.search_prenormalized(q, a, b, f, 0.5, 0.5, k=k)
@@ -120,38 +174,28 @@ def cpu_baseline(n_rows, dtype, k, max_seconds=25.0):
         no.search_prenormalized(q, a, b, f, 0.5, 0.5, k=k)
         times.append(time.perf_counter() - t0)
     best = min(times)
-    try:
-        from threadpoolctl import threadpool_info
-        threads = max([i.get("num_threads", 1) for i in threadpool_info()] or [1])
-    except Exception:
-        threads = os.cpu_count()
-    return {"value": (sample / n_rows) / best, "unit": "queries/s", "cores": int(threads),
+    return {"value": (sample / 1e6) / best, "unit": UNIT, "cores": host_threads(),
             "host_cpus": os.cpu_count(), "kind": "port",
             "sample": f"oracle/numpy_oracle.search_prenormalized (rows normalised once, 2 sgemv + fp64 fusion + "
                       f"top-k per query) on {sample} of {n_rows} segments, isotropic unit rows, best of "
-                      f"{len(times)}; scaled by segments to the full workload", "dtype": "fp32"}
+                      f"{len(times)}; per-segment cost scaled to the workload", "dtype": "fp32"}
 
 
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (oracle port; the reference itself is a
     pure-Python per-segment loop at ~0.84 ms/segment and is not present on the GPU box)."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    n_rows, dtype, nq, k, _ = WORKLOADS[args.workload]
+    n_rows, dtype, nq, k, _, _ = WORKLOADS[args.workload]
     from oracle import numpy_oracle as no
     try:        # torchrun exports OMP_NUM_THREADS=1; the CPU arm may use every host core
         from threadpoolctl import threadpool_limits
         threadpool_limits(limits=os.cpu_count())
     except Exception:
         pass
-    rng = np.random.default_rng(1)
-    sample = min(n_rows, 1_000_000)
-    a = rng.standard_normal((sample, 384), dtype=np.float32)
-    b = rng.standard_normal((sample, 384), dtype=np.float32)
-    a /= np.linalg.norm(a, axis=1, keepdims=True)
-    b /= np.linalg.norm(b, axis=1, keepdims=True)
-    f = np.full(sample, 3, np.uint8)
+    sample, a, b, f, rng = cpu_sample(n_rows)
     qs = rng.standard_normal((args.steps + args.warmup, 384)).astype(np.float32)
     qs /= np.linalg.norm(qs, axis=1, keepdims=True)
     for i in range(args.warmup):
@@ -161,40 +205,96 @@ def run_reference(args):
         no.search_prenormalized(qs[args.warmup + i], a, b, f, 0.5, 0.5, k=k)
     dt = time.perf_counter() - t0
     scale = sample / n_rows
-    val = args.steps * nq * scale / dt * (n_rows / 1e6)
-    try:
-        from threadpoolctl import threadpool_info
-        threads = max([i.get("num_threads", 1) for i in threadpool_info()] or [1])
-    except Exception:
-        threads = os.cpu_count()
-    cb = {"value": val, "unit": "queries/s (per 1M segments)", "cores": int(threads), "kind": "port",
+    val = args.steps * nq / dt * (sample / 1e6)
+    cb = {"value": val, "unit": UNIT, "cores": host_threads(), "kind": "port",
           "sample": f"each step = 1 query over {sample} of {n_rows} segments through "
                     f"oracle/numpy_oracle.search_prenormalized (vectorised restatement of audio_search.py:639-699 "
                     f"with rows normalised once at ingest; the literal reference loop runs at ~0.84 ms/segment)"}
     print(json.dumps({
-        "impl": "reference", "metric": "fused dual-corpus 384D top-k queries/s", "value": val,
-        "unit": "queries/s (per 1M segments)", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt / args.steps * 1e3 / scale, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic isotropic unit vectors",
-        "config": {"workload": args.workload, "segments_per_gpu": n_rows, "queries_per_step": nq, "k": k},
-        "cpu_baseline": cb, "e2e": {"value": val, "unit": "queries/s (per 1M segments)",
-                                    "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3 / scale, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic isotropic unit vectors",
+        "config": workload_config(args.workload, world, args.threshold),
+        "cpu_baseline": cb, "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ---- parity: the results the timed loops produced, against the oracle ---------------------------------------
+def parity_check(results, queries, wa, wb, k, dtype, n_total, n_plant_queries, plants, threshold, mode):
+    """`results`: list of (global query ids, indices[Q,k], fusion, asr, audio, count) host arrays.
+    Every returned row and every row that MUST be found is regenerated on the host and scored by
+    the oracle (audio_search.py:639-672 restated): returned scores must match, the expected rows
+    that beat the k-th score must be present, order must be (score desc, index asc).
+    Expected rows: "planted" -- the query's planted neighbours; "clustered" -- every row of the
+    query's cluster (the rest of the library is isotropic noise far below them), i.e. the full
+    answer; "ascending" -- the answer is the last k rows of the library up to fp32 near-ties."""
+    from multimodal_audio_search_b200 import synth
+    from oracle import numpy_oracle as no
+    tol = 1e-5 if dtype == "fp32" else 2e-3
+    spec = synth.plant_spec(SEED, n_total, n_plant_queries, plants) if mode == "planted" else None
+    clusters = synth.cluster_of_rows(SEED, np.arange(n_total, dtype=np.int64)) if mode == "clustered" else None
+    max_err, n_q, n_rows_checked, problems = 0.0, 0, 0, []
+    for qids, ind, fus, sa, sb, cnt in results:
+        for j, g in enumerate(qids):
+            c = int(cnt[j])
+            if c < 0 or c > k:
+                problems.append(f"query {g}: count {c}")
+                continue
+            rows = [int(r) for r in ind[j, :c]]
+            expected = []
+            if mode == "planted" and g < n_plant_queries:
+                expected = synth.plant_rows_of_query(spec, g).tolist()
+            elif mode == "clustered":
+                expected = np.nonzero(clusters == (g % synth.N_CLUSTERS))[0].tolist()
+            need = sorted(set(rows) | set(expected))
+            a, b, f, _ = synth.library(SEED, n_total, n_plant_queries, plants, False, mode=mode, rows=need)
+            o = no.search(queries[g], a, b, f, wa[g], wb[g], k=1, threshold=-1.0)
+            ca, cb = no.cosine_rows(queries[g], a), no.cosine_rows(queries[g], b)
+            truth = {r: (float(o.all_fusion[i]), float(ca[i]), float(cb[i])) for i, r in enumerate(need)}
+            if len(set(rows)) != c or (ind[j, c:] != -1).any():
+                problems.append(f"query {g}: duplicate rows or bad padding")
+            for p in range(c):
+                fu, xa, xb = truth[rows[p]]
+                e = max(abs(fus[j, p] - fu), abs(sa[j, p] - xa), abs(sb[j, p] - xb))
+                max_err = max(max_err, e)
+                if e > tol:
+                    problems.append(f"query {g} rank {p} row {rows[p]}: |err| {e:.3g}")
+                if not fus[j, p] > threshold:
+                    problems.append(f"query {g} rank {p}: score {fus[j, p]} not above the threshold")
+                if p and not (fus[j, p - 1] > fus[j, p] or (fus[j, p - 1] == fus[j, p] and rows[p - 1] < rows[p])):
+                    problems.append(f"query {g}: order broken at rank {p}")
+            kth = fus[j, c - 1] if c == k else threshold
+            for r in expected:
+                if truth[r][0] > kth + tol and r not in rows:
+                    problems.append(f"query {g}: expected row {r} (oracle score {truth[r][0]:.6f}) missing, k-th {kth:.6f}")
+            if mode == "ascending" and (c != k or min(rows) < n_total - k - 64):
+                problems.append(f"query {g}: ascending library, results {sorted(rows)[:3]}.. are not the last rows")
+            n_q += 1
+            n_rows_checked += len(need)
+    return {"ok": not problems, "queries": n_q, "rows_scored_by_oracle": n_rows_checked, "max_abs_err": max_err,
+            "tolerance": tol, "problems": problems[:5],
+            "what": "every returned row + every expected row regenerated on the host and scored by "
+                    "oracle/numpy_oracle.search; scores, completeness over the expected rows, order, padding"}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--reps", type=int, default=15, help="repetitions of the timed K-step region (median reported)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="1m_fp32_q1_top10", choices=sorted(WORKLOADS))
+    ap.add_argument("--secondary", default=None,
+                    help="comma-separated extra workloads measured in the same process ('' = none; default: the BASELINE configs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dropin", action="store_true")
     ap.add_argument("--option", action="append", default=[], help="key=value engine option")
     ap.add_argument("--threshold", type=float, default=0.1, help="relevance threshold (reference: 0.1)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: candidate exchange fused into the kernels over NVLink peer memory, or NCCL all-gather")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    args.reps = max(args.reps, 1)
     if args.impl == "reference":
         run_reference(args)
         return
@@ -209,155 +309,363 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    n_rows, dtype, nq, k, path = WORKLOADS[args.workload]
-    n_total = n_rows * world
-    plants = max(2 * k, 30)
-    n_steps = args.steps + args.warmup
-
-    idx = SegmentIndex(dtype, capacity=n_rows, device=local)
-    for kv in args.option:
-        key, v = kv.split("=")
-        idx.set_option(key, int(v))
-    t_build = time.perf_counter()
-    idx.append_synth(SEED, n_total, rank * n_rows, (rank + 1) * n_rows, n_queries=min(n_steps * nq, 4096), plants=plants)
-    idx.row_base = rank * n_rows
-    t_build = time.perf_counter() - t_build
-
-    # step i uses queries [i*nq, (i+1)*nq) -- distinct per step; weights cycle over the classes
-    q_host = synth.raw_queries(SEED, 0, n_steps * nq)
-    w_classes = [0.5, 0.2, 0.3, 0.4, 0.6, 0.7, 0.8]
-    wa_all = np.array([w_classes[i % len(w_classes)] for i in range(n_steps * nq)])
-    wb_all = 1.0 - wa_all
-    q_dev = torch.from_numpy(q_host).cuda()
-    exchange = args.exchange
-    try:
-        sharded = ShardedSearcher(idx, rank, world, exchange=exchange, max_queries=max(nq, 1), max_k=k)
-        ok = 1
-    except Exception as e:          # e.g. CUDA IPC not permitted in this container: use the NCCL all-gather
-        ok = 0
-        if rank == 0:
-            print(f"bench: peer-memory exchange unavailable ({e}); using NCCL all-gather", file=sys.stderr)
-    if world > 1:
-        t_ok = torch.tensor([ok], device="cuda")
-        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
-        if int(t_ok.item()) == 0:
-            exchange = "nccl"
-            sharded = ShardedSearcher(idx, rank, world, exchange="nccl")
-
-    def step_device(i):
-        sl = slice(i * nq, (i + 1) * nq)
-        if world == 1:
-            return idx.search(q_dev[sl], wa_all[sl], wb_all[sl], k=k, path=path, threshold=args.threshold)
-        return sharded.search(q_dev[sl], wa_all[sl], wb_all[sl], k=k, threshold=args.threshold, path=path, to_host=False)
-
-    def step_host(i):
-        sl = slice(i * nq, (i + 1) * nq)
-        if world == 1:
-            return idx.search(q_host[sl], wa_all[sl], wb_all[sl], k=k, path=path, threshold=args.threshold)
-        return sharded.search(q_host[sl], wa_all[sl], wb_all[sl], k=k, threshold=args.threshold, path=path, to_host=True)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    def max_over_ranks(values):
+        t = torch.tensor(values, dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.cpu().numpy()
 
-    # ---- device-resident throughput (`value`) ---------------------------------------------------
-    for i in range(args.warmup):
-        step_device(i)
     sampler = ClockSampler(local)
-    barrier()
     if rank == 0:
-        sampler.start()
-    launches0 = idx.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        last = step_device(args.warmup + i)
-    e1.record()
-    barrier()
-    launches = idx.launch_count - launches0
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    ms_step = ms_total / args.steps
+        sampler.start()         # before any barrier: forking nvidia-smi must not skew rank 0 against the others
+    hbm_peak, tc_burst, tc_sustained, peak_src = peaks()
+    exchange_state = {"kind": args.exchange}
 
-    # ---- end to end through the public host API (`e2e`): host query in, host results out ---------
-    for i in range(3):
-        step_host(i)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        last_host = step_host(args.warmup + i)
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    clocks = sampler.stop() if rank == 0 else None
+    def measure(name, reps, with_cpu, with_dropin):
+        n_rows, dtype, nq, k, path, mode = WORKLOADS[name]
+        n_total = n_rows * world
+        plants = max(2 * k, 30)
+        steps = args.steps
+        n_steps = steps + args.warmup
+        n_plant_queries = min(n_steps * nq, 4096)
+        idx = SegmentIndex(dtype, capacity=n_rows, device=local)
+        for kv in args.option:
+            key, v = kv.split("=")
+            idx.set_option(key, int(v))
+        t_build = time.perf_counter()
+        idx.append_synth(SEED, n_total, rank * n_rows, (rank + 1) * n_rows, n_queries=n_plant_queries, plants=plants, mode=mode)
+        idx.row_base = rank * n_rows
+        t_build = time.perf_counter() - t_build
 
-    # ---- scan-kernel time (roofline): CUDA events around the scan launch, on its stream ----------
-    idx.set_option("time_kernels", 1)
-    scan_ms = []
-    for i in range(min(args.steps, 50)):
-        step_device(args.warmup + i)
-        scan_ms.append(idx.last_scan_ms())
-    idx.set_option("time_kernels", 0)
-    scan_ms = float(np.mean(scan_ms))
-    scan_ms = max_over_ranks(scan_ms)
+        # step i uses queries [i*nq, (i+1)*nq) -- distinct per step; weights cycle over the classes
+        q_host = synth.bench_queries(SEED, mode, 0, n_steps * nq)
+        wa_all = np.array([W_CLASSES[i % len(W_CLASSES)] for i in range(n_steps * nq)])
+        wb_all = 1.0 - wa_all
+        q_dev = torch.from_numpy(q_host).cuda()
+        sharded = None
+        if world > 1:
+            try:
+                sharded = ShardedSearcher(idx, rank, world, exchange=exchange_state["kind"], max_queries=max(nq, 1), max_k=k)
+                ok = 1
+            except Exception as e:      # e.g. CUDA IPC not permitted in this container: use the NCCL all-gather
+                ok = 0
+                if rank == 0:
+                    print(f"bench: peer-memory exchange unavailable ({e}); using NCCL all-gather", file=sys.stderr)
+            t_ok = torch.tensor([ok], device="cuda")
+            dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+            if int(t_ok.item()) == 0:
+                exchange_state["kind"] = "nccl"
+                sharded = ShardedSearcher(idx, rank, world, exchange="nccl")
 
-    if rank == 0:
-        hbm_peak, tc_burst, tc_sustained, peak_src = peaks()
-        norm = n_total / 1e6
-        value = nq * 1e3 / ms_step * norm
-        e2e_value = args.steps * nq / e2e_s * norm
-        alg_bytes = n_rows * bytes_per_row(dtype)            # per launch (one rank's scan)
-        if path == "gemm":
-            flops = nq * n_rows * 4 * 384
-            achieved = flops / (scan_ms * 1e-3) / 1e12
-            # back-to-back tensor-core steps run under the 1 kW power cap: the sustained cuBLAS figure is
-            # the matching denominator (B200_PROFILING.md); the burst fraction is reported beside it.
-            roof = {"bound": "tensor", "achieved": achieved, "peak": tc_sustained, "unit": "TFLOP/s",
-                    "frac": achieved / tc_sustained, "peak_kind": "sustained cuBLAS bf16 (kernel timed inside a long step)",
-                    "frac_of_burst_peak": achieved / tc_burst, "frac_of_2250_nominal": achieved / 2250.0,
-                    "traffic": None, "peak_source": peak_src, "kernel": "gemm_scan_kernel", "kernel_ms": scan_ms,
-                    "algorithmic_flops_per_launch": flops, "hbm_gbs": alg_bytes / (scan_ms * 1e-3) / 1e9}
+        def step_device(i):
+            sl = slice(i * nq, (i + 1) * nq)
+            if world == 1:
+                return idx.search(q_dev[sl], wa_all[sl], wb_all[sl], k=k, path=path, threshold=args.threshold)
+            return sharded.search(q_dev[sl], wa_all[sl], wb_all[sl], k=k, threshold=args.threshold, path=path, to_host=False)
+
+        def step_host(i):
+            sl = slice(i * nq, (i + 1) * nq)
+            if world == 1:
+                return idx.search(q_host[sl], wa_all[sl], wb_all[sl], k=k, path=path, threshold=args.threshold)
+            return sharded.search(q_host[sl], wa_all[sl], wb_all[sl], k=k, threshold=args.threshold, path=path, to_host=True)
+
+        # ---- device-resident throughput (`value`): R repetitions of the K-step region -------------------
+        # The query batch is resident in HBM and complete before the loop starts: "queries_settled"
+        # lets the scan of step i+1 start while step i's finalize / exchange / merge is in flight.
+        idx.set_option("queries_settled", 1)
+        for i in range(args.warmup):
+            step_device(i)
+        t_win0 = sampler.mark()
+        launches0 = idx.launch_count
+        rep_ms, keep = [], []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e0.record()
+            for i in range(steps):
+                last = step_device(args.warmup + i)
+                if i >= steps - 2:
+                    keep.append((i, last))
+            e1.record()
+            barrier()
+            rep_ms.append(e0.elapsed_time(e1))
+            keep = keep[-2:]
+        launches = (idx.launch_count - launches0) // reps
+        idx.set_option("queries_settled", 0)
+        rep_ms = max_over_ranks(rep_ms)                         # per repetition: max over ranks
+        ms_step = float(np.median(rep_ms)) / steps
+
+        # ---- end to end through the public host API (`e2e`): host query in, host results out ---------
+        for i in range(3):
+            step_host(i)
+        e2e_s, keep_host = [], []
+        for _ in range(reps):
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(steps):
+                last_host = step_host(args.warmup + i)
+                if i >= steps - 2:
+                    keep_host.append((i, last_host))
+            torch.cuda.synchronize()
+            e2e_s.append(time.perf_counter() - t0)
+            keep_host = keep_host[-2:]
+        barrier()
+        e2e_s = max_over_ranks(e2e_s)
+        e2e_step_s = float(np.median(e2e_s)) / steps
+        t_win1 = sampler.mark()
+
+        # ---- scan-kernel time (roofline): CUDA events around the scan launch, on its stream ----------
+        idx.set_option("time_kernels", 1)
+        scan_ms = []
+        for i in range(min(steps, 50)):
+            step_device(args.warmup + i)
+            scan_ms.append(idx.last_scan_ms())
+        idx.set_option("time_kernels", 0)
+        scan_ms = float(max_over_ranks([float(np.mean(scan_ms))])[0])
+
+        # ---- exchange breakdown (N > 1): %globaltimer stamps inside the finalize kernel -----------------
+        breakdown = None
+        if world > 1 and exchange_state["kind"] == "p2p":
+            idx.set_option("stamp_exchange", 1)
+            idx.set_option("queries_settled", 1)
+            barrier()
+            for i in range(min(steps, 48)):
+                step_device(args.warmup + i)
+            barrier()
+            st = idx.exchange_stamps(64).astype(np.int64)
+            idx.set_option("stamp_exchange", 0)
+            idx.set_option("queries_settled", 0)
+            if len(st) > 8:
+                st = st[4:]
+                d = np.stack([st[:, 1] - st[:, 0], st[:, 2] - st[:, 1], st[:, 3] - st[:, 2], st[:, 3] - st[:, 0]], 1) / 1e3
+                mine = d.mean(0).tolist()
+                worst = max_over_ranks(mine)
+                breakdown = {"unit": "us per step, mean over the stamped steps",
+                             "rank0": {"select_rescore_push_flag": mine[0], "wait_for_all_flags": mine[1], "merge_emit": mine[2], "total_after_scan": mine[3]},
+                             "max_over_ranks": {"select_rescore_push_flag": float(worst[0]), "wait_for_all_flags": float(worst[1]),
+                                                "merge_emit": float(worst[2]), "total_after_scan": float(worst[3])},
+                             "how": "%globaltimer read inside finalize_kernel at scan-complete, own-flag-raised, all-flags-seen, results-written"}
+
+        # ---- parity of what was just timed ---------------------------------------------------------------
+        def to_host(res):
+            g = lambda t: t.cpu().numpy() if hasattr(t, "cpu") else np.asarray(t)
+            return g(res.indices), g(res.fusion), g(res.asr_sim), g(res.audio_sim), g(res.count)
+        check_q = 8 if nq > 8 else nq               # tensor-core batches: 8 queries spread over the batch
+        picked = []
+        for i, res in keep + keep_host:
+            ind, fus, sa, sb, cnt = to_host(res)
+            sel = np.linspace(0, nq - 1, check_q).astype(int)
+            step_q0 = (args.warmup + i) * nq
+            picked.append(([step_q0 + int(s) for s in sel], ind[sel], fus[sel], sa[sel], sb[sel], cnt[sel]))
+        parity = None
+        if rank == 0:
+            parity = parity_check(picked, q_host, wa_all, wb_all, k, dtype, n_total, n_plant_queries, plants, args.threshold, mode)
+            same = all(np.array_equal(to_host(a[1])[0], to_host(b[1])[0]) and np.array_equal(to_host(a[1])[1], to_host(b[1])[1])
+                       for a, b in zip(keep, keep_host))
+            parity["device_path_equals_host_path"] = bool(same)
+            parity["ok"] = bool(parity["ok"] and same)
+        if world > 1:
+            # every rank must hold the same merged answer
+            ind0 = torch.from_numpy(np.ascontiguousarray(to_host(keep[-1][1])[0])).cuda()
+            lo, hi = ind0.clone(), ind0.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            if rank == 0:
+                parity["all_ranks_hold_the_same_result"] = bool(torch.equal(lo, hi))
+                parity["ok"] = bool(parity["ok"] and parity["all_ranks_hold_the_same_result"])
+
+        out = None
+        if rank == 0:
+            norm = n_total / 1e6
+            alg_bytes = n_rows * bytes_per_row(dtype)            # one rank's scan reads its shard once per launch
+            if path == "gemm":
+                flops = nq * n_rows * 4 * 384
+                achieved = flops / (scan_ms * 1e-3) / 1e12
+                # back-to-back tensor-core steps run under the 1 kW power cap: the sustained cuBLAS figure is
+                # the matching denominator (B200_PROFILING.md); the burst fraction is reported beside it.
+                roof = {"bound": "tensor", "achieved": achieved, "peak": tc_sustained, "unit": "TFLOP/s",
+                        "frac": achieved / tc_sustained, "peak_kind": "sustained cuBLAS bf16 (kernel timed inside a long step)",
+                        "frac_of_burst_peak": achieved / tc_burst, "frac_of_2250_nominal": achieved / 2250.0,
+                        "peak_source": peak_src, "kernel": "gemm_scan_kernel", "kernel_ms": scan_ms,
+                        "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": alg_bytes,
+                        "hbm_gbs": alg_bytes / (scan_ms * 1e-3) / 1e9}
+                hbm_all = world * alg_bytes / (ms_step * 1e-3) / 1e9      # the batch reads the corpus ONCE
+            else:
+                achieved = alg_bytes * nq / (scan_ms * 1e-3) / 1e9
+                roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": achieved / hbm_peak, "frac_of_8TBps_spec": achieved / 8000.0,
+                        "peak_source": peak_src, "kernel": "cab_scan_kernel", "kernel_ms": scan_ms,
+                        "algorithmic_bytes_per_launch": alg_bytes * nq}
+                hbm_all = world * alg_bytes * nq / (ms_step * 1e-3) / 1e9
+            tfile = os.path.join(ROOT, "profiles", "traffic.json")
+            roof["traffic"] = None
+            if os.path.exists(tfile):
+                t = json.load(open(tfile)).get(name)
+                if t:
+                    roof["traffic"] = t
+                    roof["traffic_source"] = "static: profiles/traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel on this workload; not re-measured in this run)"
+            out = {
+                "metric": METRIC, "value": nq * 1e3 / ms_step * norm, "unit": UNIT, "n_gpus": world, "steps": steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None,
+                "dtype": "f32" if dtype == "fp32" else "bf16 storage, f32 accumulate",
+                "data": "synthetic (integer-hash rows, %s); the reference arm uses isotropic unit rows of the same shape" % (
+                    "planted neighbours" if mode == "planted" else mode),
+                "config": workload_config(name, world, args.threshold),
+                "exchange": "none" if world == 1 else (
+                    "per-shard top-k (24 B x k x Q per rank) stored into every rank's buffer over NVLink peer memory, epoch "
+                    "flag, wait and merge all inside the finalize kernel; the next step's scan overlaps it"
+                    if exchange_state["kind"] == "p2p" else "NCCL all_gather of per-shard top-k (24 B x k x Q per rank) + device merge"),
+                "repetitions": {"n": reps, "statistic": "median", "ms_per_step_min": float(rep_ms.min()) / steps,
+                                "ms_per_step_max": float(rep_ms.max()) / steps,
+                                "what": "each repetition = barrier + synchronize, CUDA event, K steps, CUDA event, barrier + "
+                                        "synchronize; max over ranks per repetition, median over repetitions"},
+                "queries_per_s": nq * 1e3 / ms_step, "hbm_gbs_all_gpus": hbm_all,
+                "e2e": {"value": nq / e2e_step_s * norm, "unit": UNIT, "ms_per_step": e2e_step_s * 1e3,
+                        "ms_per_step_min": float(e2e_s.min()) / steps * 1e3, "ms_per_step_max": float(e2e_s.max()) / steps * 1e3,
+                        "h2d_bytes_per_step": nq * 384 * 4 + nq * 24,
+                        "d2h_bytes_per_step": nq * k * (8 + 8 + 4 + 4 + 1) + nq * 4 + 4,
+                        "api": "SegmentIndex.search / ShardedSearcher.search (C-ABI cab_search / cab_search_sharded), numpy in, numpy out"},
+                "gpu_launches": int(launches), "roofline": roof, "clocks": sampler.window(t_win0, t_win1),
+                "parity_check": parity, "build_s": t_build,
+            }
+            if breakdown:
+                out["exchange_breakdown"] = breakdown
+            if with_cpu:
+                out["cpu_baseline"] = cpu_baseline(n_rows, dtype, k)
+        if with_dropin and world == 1 and nq == 1:
+            d = dropin_e2e(idx, n_rows, dtype, q_host, steps, args.warmup, n_plant_queries, plants)
+            if out is not None:
+                out["e2e_dropin"] = d
         else:
-            achieved = alg_bytes * nq / (scan_ms * 1e-3) / 1e9
-            roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": achieved / hbm_peak, "frac_of_8TBps_spec": achieved / 8000.0, "traffic": None,
-                    "peak_source": peak_src, "kernel": "gemv_scan_kernel", "kernel_ms": scan_ms,
-                    "algorithmic_bytes_per_launch": alg_bytes * nq}
-        tfile = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tfile):
-            roof["traffic"] = json.load(open(tfile)).get(args.workload)
-        out = {
-            "metric": "fused dual-corpus 384D top-k queries/s", "value": value,
-            "unit": "queries/s (per 1M segments)", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if dtype == "fp32" else "bf16 storage, f32 accumulate", "data": "synthetic (integer-hash rows, planted neighbours)",
-            "config": {"workload": args.workload, "segments_per_gpu": n_rows, "global_segments": n_total,
-                       "queries_per_step": nq, "k": k, "path": path, "threshold": args.threshold,
-                       "l2": "inputs larger than L2 (corpus bytes per GPU >> 126 MB)",
-                       "exchange": "none" if world == 1 else (
-                           "per-shard top-k (24 B x k x Q per rank) stored into every rank's buffer over NVLink peer memory "
-                           "inside the finalize kernel + flag wait in the merge kernel" if exchange == "p2p" else
-                           "NCCL all_gather of per-shard top-k (24 B x k x Q per rank) + device merge"),
-                       "value_definition": "queries/s x global_segments/1e6"},
-            "queries_per_s": nq * 1e3 / ms_step, "hbm_gbs_all_gpus": world * alg_bytes * nq / (ms_step * 1e-3) / 1e9,
-            "e2e": {"value": e2e_value, "unit": "queries/s (per 1M segments)", "ms_per_step": e2e_s / args.steps * 1e3,
-                    "h2d_bytes_per_step": nq * 384 * 4 + nq * 24,
-                    "d2h_bytes_per_step": nq * k * (8 + 8 + 4 + 4 + 1) + nq * 4 + 4},
-            "gpu_launches": int(launches), "roofline": roof, "clocks": clocks,
-            "build_s": t_build,
-        }
-        if not args.no_cpu_baseline and world == 1:      # the CPU baseline is reported at N=1 only
-            out["cpu_baseline"] = cpu_baseline(n_rows, dtype, k)
-        print(json.dumps(out))
+            idx.close()
+        del q_dev
+        torch.cuda.empty_cache()
+        return out
+
+    def dropin_e2e(idx, n_rows, dtype, q_host, steps, warmup, n_plant_queries, plants):
+        """The reference-facing call: DualPipelineAudioSearch.search_with_fusion(str) over the same
+        1M-row library (columnar segment table), with a stand-in embedder that returns the
+        synthetic query vector -- keyword weight analysis, embedder hand-off, search, result dicts."""
+        from multimodal_audio_search_b200 import DualPipelineAudioSearch
+        from multimodal_audio_search_b200.segment_table import SegmentTable
+        texts = ["someone speaking about the weather", "piano music with drums", "what did she say about the meeting",
+                 "loud engine noise", "a conversation with background music", "xyzzy"]
+
+        class Embedder:
+            def __init__(self):
+                self.i = 0
+
+            def encode(self, text):
+                v = q_host[self.i % len(q_host)]
+                self.i += 1
+                return v
+        eng = DualPipelineAudioSearch(dtype=dtype, device=local, text_embedder=Embedder())
+        table = SegmentTable.from_columns(n_rows)
+        eng._cab_library.adopt(idx, table)
+        eng.audio_segments = table
+        for i in range(warmup):
+            eng.search_with_fusion(texts[i % len(texts)])
+        eng.text_embedder.i = warmup
+        t0 = time.perf_counter()
+        n_res = 0
+        for i in range(steps):
+            results, info = eng.search_with_fusion(texts[i % len(texts)])
+            n_res += len(results)
+        dt = time.perf_counter() - t0
+        # parity of the drop-in: its dicts against the oracle on regenerated rows
+        from multimodal_audio_search_b200 import synth as sy
+        from oracle import numpy_oracle as no
+        eng.text_embedder.i = 7
+        results, info = eng.search_with_fusion(texts[1])
+        ok, err = bool(results), 0.0
+        for r in results:
+            row = int(round(r["start_time"] / 5.0))
+            a, b, f, _ = sy.library(SEED, n_rows, n_plant_queries, plants, False, r0=row, r1=row + 1)
+            o = no.search(q_host[7], a, b, f, info["asr_weight"], info["audio_weight"], k=1, threshold=-1.0)
+            err = max(err, abs(r["fusion_score"] - float(o.all_fusion[0])))
+        ok = ok and err <= (1e-5 if dtype == "fp32" else 2e-3)
+        idx_rows = len(eng._cab_library.index)
+        eng._cab_library.index.close()
+        return {"value": steps / dt * (n_rows / 1e6), "unit": UNIT, "ms_per_step": dt / steps * 1e3,
+                "api": "DualPipelineAudioSearch.search_with_fusion(str) -> (results[:10], weight_info) "
+                       "(audio_search.py:624 signature; stand-in embedder returns the synthetic vector)",
+                "segments": idx_rows, "results_per_query": n_res / steps,
+                "parity_check": {"ok": bool(ok), "max_abs_err": err}}
+
+    # ---- N > 1: the sharded answer against ONE index over the same global rows ------------------------------
+    def cross_check():
+        per, nq, k = 60_000, 40, 10
+        n_total = per * world
+        whole = SegmentIndex("fp32", capacity=n_total, device=local)
+        whole.append_synth(SEED + 1, n_total, 0, n_total, n_queries=nq, plants=30, partial=True)
+        part = SegmentIndex("fp32", capacity=per, device=local)
+        part.append_synth(SEED + 1, n_total, rank * per, (rank + 1) * per, n_queries=nq, plants=30, partial=True)
+        part.row_base = rank * per
+        sh = ShardedSearcher(part, rank, world, exchange=exchange_state["kind"], max_queries=64, max_k=100)
+        q = synth.raw_queries(SEED + 1, 0, nq)
+        qd = torch.from_numpy(q).cuda()
+        wa = np.array([W_CLASSES[i % len(W_CLASSES)] for i in range(nq)]); wb = 1.0 - wa
+        bad, n = 0, 0
+        cases = [(i, i + 1, 10) for i in range(8)] + [(8, 9, 100), (0, 40, 10), (9, 10, 10), (0, 40, 100)]
+        for lo, hi, kk in cases:
+            want = whole.search(q[lo:hi], wa[lo:hi], wb[lo:hi], k=kk)
+            got = sh.search(qd[lo:hi], wa[lo:hi], wb[lo:hi], k=kk, to_host=False)
+            goth = sh.search(q[lo:hi], wa[lo:hi], wb[lo:hi], k=kk, to_host=True)
+            for g in (got, goth):
+                gi = g.indices.cpu().numpy() if hasattr(g.indices, "cpu") else g.indices
+                gf = g.fusion.cpu().numpy() if hasattr(g.fusion, "cpu") else g.fusion
+                bad += int(not (np.array_equal(gi, want.indices) and np.array_equal(gf, want.fusion)))
+                n += hi - lo
+        t = torch.tensor([bad], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        torch.cuda.synchronize()
+        dist.barrier()
+        whole.close(); part.close()
+        return {"ok": int(t.item()) == 0, "queries": n, "mismatching_calls_over_all_ranks": int(t.item()),
+                "what": f"{world} x {per} segments: ShardedSearcher ({exchange_state['kind']}) on every rank vs one index "
+                        f"over all rows on the same rank, bit-exact indices and float64 fusion scores, fused and separate merge"}
+
+    line = measure(args.workload, args.reps, with_cpu=not args.no_cpu_baseline and world == 1, with_dropin=not args.no_dropin)
     if world > 1:
+        cc = cross_check()
+        if rank == 0:
+            line["parity_check"]["sharded_vs_single_index"] = cc
+            line["parity_check"]["ok"] = bool(line["parity_check"]["ok"] and cc["ok"])
+    sec_names = SECONDARY[1 if world == 1 else "multi"] if args.secondary is None else [s for s in args.secondary.split(",") if s]
+    secondary = []
+    for name in sec_names:
+        if name == args.workload:
+            continue
+        r = measure(name, max(3, min(args.reps, 7)), with_cpu=False, with_dropin=False)
+        if rank == 0:
+            secondary.append({k: r[k] for k in ("config", "dtype", "value", "unit", "ms_per_step", "queries_per_s", "repetitions",
+                                                "e2e", "roofline", "clocks", "parity_check", "gpu_launches", "hbm_gbs_all_gpus")
+                              if k in r} | ({"exchange_breakdown": r["exchange_breakdown"]} if "exchange_breakdown" in r else {}))
+    if rank == 0:
+        sampler.stop()
+        line["secondary"] = secondary
+        ok = line["parity_check"]["ok"] and all(s["parity_check"]["ok"] for s in secondary)
+        if "e2e_dropin" in line:
+            ok = ok and line["e2e_dropin"]["parity_check"]["ok"]
+        print(json.dumps(line))
+        if not ok:
+            print("bench: PARITY CHECK FAILED -- the numbers above are void", file=sys.stderr)
+    else:
+        ok = True
+    if world > 1:
+        flag = torch.tensor([0 if ok else 1], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        ok = int(flag.item()) == 0
         dist.barrier()
         dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
 
 
 if __name__ == "__main__":

@@ -103,7 +103,9 @@ CAB_API int cab_index_append(cab_index *idx, const float *asr_rows, const float 
 
 /* Append global rows [r0, r1) of the deterministic synthetic library (seed, n_total rows,
  * planted neighbours, optional partial flags) generated ON DEVICE; bit-identical to
- * multimodal_audio_search_b200/synth.py.  Benchmark/test data source (BASELINE.json configs). */
+ * multimodal_audio_search_b200/synth.py.  Benchmark/test data source (BASELINE.json configs).
+ * `partial`: bit 0 = ~10 % ASR-only / ~10 % audio-only rows; bits 8-15 = distribution: 0 planted
+ * neighbours over isotropic noise, 1 "ascending" scores (defeats top-k pruning), 2 "clustered". */
 CAB_API int cab_index_append_synth(cab_index *idx, uint32_t seed, int64_t n_total, int64_t r0, int64_t r1,
                            int n_queries, int plants, int partial, void *stream);
 /* Raw synthetic query vectors [q0, q1) as fp32 [n x dim] into `out` (host or device). */

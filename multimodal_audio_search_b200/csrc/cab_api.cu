@@ -366,7 +366,11 @@ int cab_index_append_synth(cab_index *idx, uint32_t seed, int64_t n_total, int64
         if (rc == CAB_ERR_NOMEM && idx->capacity * 2 > idx->size + n_rows) rc = grow(idx, idx->size + n_rows);   // ... or exact fit
         if (rc != CAB_OK) return rc;
     }
-    const SynthParams p = make_synth(seed, n_total, n_queries, plants);
+    const int mode = (partial >> 8) & 0xFF;
+    partial &= 1;
+    if (mode > 2) return fail(idx, CAB_ERR_INVALID, "unknown synthetic distribution %d", mode);
+    SynthParams p = make_synth(seed, n_total, n_queries, mode == 0 ? plants : 0);
+    p.mode = mode;
     const int64_t chunk = 65536;
     const size_t need = size_t(chunk) * CAB_DIM * sizeof(float);
     if (idx->d_rows_bytes < need) {

@@ -99,6 +99,10 @@ __device__ __forceinline__ float synth_elem(uint32_t row_key, int j) {
 
 // `partial`: rows whose pipeline "failed" (flag bit clear, see synth.row_flags) have no embedding
 // in the reference (None, audio_search.py:344/350) -> an all-zero row here.
+// p.mode: 0 planted neighbours over isotropic noise; 1 "ascending" (every row scores a hair above
+// its predecessor: the adversarial order for a pruning scan); 2 "clustered" (1024 shared centres).
+// Twin of synth.corpus_rows_at -- bit-identical, so every fp32 operation of mode 1 is spelled out
+// with its rounding (no FMA contraction).
 __global__ void __launch_bounds__(256) synth_rows_kernel(SynthParams p, int stream_id, int partial,
                                                          int64_t r0, int64_t n, float *__restrict__ out) {
     const int lane = threadIdx.x & 31;
@@ -107,6 +111,11 @@ __global__ void __launch_bounds__(256) synth_rows_kernel(SynthParams p, int stre
     const uint32_t skey = stream_key(p.seed, uint32_t(stream_id));
     const uint32_t qkey = stream_key(p.seed, 2u);
     const uint32_t fkey = stream_key(p.seed, 3u);
+    const uint32_t ckey = stream_key(p.seed, 4u);                          // cluster of a row
+    const uint32_t d_rk = mix32(qkey);                                     // raw query 0: the ascent direction
+    const uint32_t e_rk = mix32(stream_key(p.seed, 5u + uint32_t(stream_id)));   // second axis of this corpus's plane
+    const uint32_t centre_key = stream_key(p.seed, 8u);
+    const float asc_step = __fdiv_rn(0.8f, __ull2float_rn(p.n_total > 1 ? p.n_total - 1 : 1ull));
     for (int64_t i = warp; i < n; i += n_warps) {
         const uint64_t r = uint64_t(r0 + i);
         const uint32_t rk = mix32(skey ^ uint32_t(r));
@@ -118,6 +127,25 @@ __global__ void __launch_bounds__(256) synth_rows_kernel(SynthParams p, int stre
                 for (int c = 0; c < kDim / 32; ++c) out[i * kDim + lane + 32 * c] = 0.f;
                 continue;
             }
+        }
+        if (p.mode == 1) {
+            const float alpha = __fadd_rn(0.15f, __fmul_rn(__ull2float_rn(r), asc_step));
+            const float beta = __fsqrt_rn(__fsub_rn(1.0f, __fmul_rn(alpha, alpha)));
+#pragma unroll
+            for (int c = 0; c < kDim / 32; ++c) {
+                const int j = lane + 32 * c;
+                out[i * kDim + j] = __fadd_rn(__fmul_rn(alpha, synth_elem(d_rk, j)), __fmul_rn(beta, synth_elem(e_rk, j)));
+            }
+            continue;
+        }
+        if (p.mode == 2) {
+            const uint32_t crk = mix32(centre_key ^ (mix32(ckey ^ uint32_t(r)) % 1024u));
+#pragma unroll
+            for (int c = 0; c < kDim / 32; ++c) {
+                const int j = lane + 32 * c;
+                out[i * kDim + j] = 3.0f * synth_elem(crk, j) + 2.0f * synth_elem(rk, j);   // exact: small integers
+            }
+            continue;
         }
         float m = 0.f, nn = 1.f;
         uint32_t qrk = 0;

@@ -30,6 +30,7 @@ struct SynthParams {
     uint32_t n_plants_total;   // n_queries * plants
     uint32_t plants;           // per query
     uint64_t base, inv_stride;
+    int mode;                  // 0 planted, 1 ascending, 2 clustered (synth.MODES)
 };
 void launch_synth_rows(const SynthParams &p, int stream_id, int partial, int64_t r0, int64_t n,
                        float *out, cudaStream_t s);

@@ -174,11 +174,13 @@ class SegmentIndex:
         N.check(self._lib.cab_index_append(self._h, _ptr(a), _ptr(b), _ptr(f), n, N.CAB_HOST, None), self._h)
 
     def append_synth(self, seed: int, n_total: int, r0: int = 0, r1: int | None = None,
-                     n_queries: int = 1, plants: int = 0, partial: bool = False):
-        """Generate global rows [r0, r1) of the synthetic library on the device (synth.py twin)."""
+                     n_queries: int = 1, plants: int = 0, partial: bool = False, mode: str = "planted"):
+        """Generate global rows [r0, r1) of the synthetic library on the device (synth.py twin);
+        `mode`: "planted" | "ascending" | "clustered" (synth.MODES)."""
+        from .synth import MODES
         r1 = n_total if r1 is None else r1
         N.check(self._lib.cab_index_append_synth(self._h, seed & 0xFFFFFFFF, n_total, r0, r1,
-                                                 n_queries, plants, int(bool(partial)), None), self._h)
+                                                 n_queries, plants, int(bool(partial)) | (MODES[mode] << 8), None), self._h)
 
     def read_rows(self, corpus: int, r0: int, r1: int) -> np.ndarray:
         out = np.empty((r1 - r0, self.dim), dtype=np.float32)
