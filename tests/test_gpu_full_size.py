@@ -18,15 +18,14 @@ pytestmark = pytest.mark.gpu
 N_ROWS, SEED, PLANTS = 10_000_000, 20261018, 24
 
 
-def _planted_truth(qi, q, wa, wb, n_queries):
+def _planted_truth(qi, q, wa, wb, n_queries, plants=PLANTS):
     """Oracle fused scores of query qi's planted rows: {global row: (fusion, s_asr, s_audio)}."""
-    spec = synth.plant_spec(SEED, N_ROWS, n_queries, PLANTS)
-    out = {}
-    for r in synth.plant_rows_of_query(spec, qi).tolist():
-        a, b, f, _ = synth.library(SEED, N_ROWS, n_queries, PLANTS, False, r0=r, r1=r + 1)
-        o = no.search(q, a, b, f, wa, wb, k=1, threshold=-1.0)
-        out[r] = (float(o.all_fusion[0]), float(no.cosine_rows(q, a)[0]), float(no.cosine_rows(q, b)[0]))
-    return out
+    spec = synth.plant_spec(SEED, N_ROWS, n_queries, plants)
+    rows = synth.plant_rows_of_query(spec, qi).tolist()
+    a, b, f, _ = synth.library(SEED, N_ROWS, n_queries, plants, False, rows=rows)
+    o = no.search(q, a, b, f, wa, wb, k=1, threshold=-1.0)
+    sa, sb = no.cosine_rows(q, a), no.cosine_rows(q, b)
+    return {r: (float(o.all_fusion[i]), float(sa[i]), float(sb[i])) for i, r in enumerate(rows)}
 
 
 def _check_properties(res, i, threshold=0.1):
@@ -68,7 +67,7 @@ def test_10m_bf16_batch256_top100_tensor_cores():
     again = idx.search(q, wa, wb, k=k, path="gemm")
     assert gm.indices.tolist() == again.indices.tolist()
     assert (gm.count == k).all()
-    for i in (0, 1, 100, 255):
+    for i in range(nq):                                             # every query of the batch
         gi, gf = _check_properties(gm, i)
         truth = _planted_truth(i, q[i], wa[i], wb[i], nq)
         got = dict(zip(gi.tolist(), gf.tolist()))
@@ -123,3 +122,55 @@ def test_10m_legacy_scores_are_bit_exact_combinations():
         assert np.abs(half[qi][gi] - gf).max() <= 1e-6
         assert all(half[qi][i] >= kth - 1e-6 for i in gi)
     idx.close()
+
+
+def test_config5_weight_sweep_recall_at_10():
+    """BASELINE.json configs[4]: keyword-weight sweep (ASR weight 0.2 ... 0.8, the classes
+    audio_search.py:593-620 can produce) over a 10 M-segment library, 4096 mixed queries; recall@10
+    of the bf16 tensor-core engine against the fp32 reference ordering, |score error| <= 2e-3.
+    The reference ordering is anchored on the ORACLE: for every query the oracle scores the query's
+    planted rows (regenerated on the host); the fp32 list must carry every planted row that beats
+    its k-th score, at the oracle's score (1e-5) -- only the non-planted ranks (isotropic noise
+    rows that happen to reach the top-10) rest on the fp32 engine alone."""
+    import torch
+    nq, k, plants = 4096, 10, 20
+    W = [0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8]
+    q = synth.raw_queries(SEED, 0, nq)
+    wa = np.array([W[i % len(W)] for i in range(nq)]); wb = 1.0 - wa
+    qd = torch.from_numpy(q).cuda()
+    f32 = SegmentIndex("fp32", capacity=N_ROWS)
+    f32.append_synth(SEED, N_ROWS, 0, N_ROWS, n_queries=nq, plants=plants)
+    ref_i, ref_f = [], []
+    for i in range(0, nq, 32):
+        r = f32.search(qd[i:i + 32], wa[i:i + 32], wb[i:i + 32], k=k, path="gemv")
+        ref_i.append(r.indices.cpu().numpy()); ref_f.append(r.fusion.cpu().numpy())
+    f32.close()
+    ref_i, ref_f = np.concatenate(ref_i), np.concatenate(ref_f)
+    bf = SegmentIndex("bf16", capacity=N_ROWS)
+    bf.append_synth(SEED, N_ROWS, 0, N_ROWS, n_queries=nq, plants=plants)
+    g = bf.search(qd, wa, wb, k=k, path="gemm")
+    got_i, got_f = g.indices.cpu().numpy(), g.fusion.cpu().numpy()
+    bf.close()
+    hits = np.zeros(nq); tot = np.zeros(nq)
+    max_err, oracle_rows = 0.0, 0
+    for i in range(nq):
+        truth = _planted_truth(i, q[i], wa[i], wb[i], nq, plants)
+        ref = {int(r): float(s) for r, s in zip(ref_i[i], ref_f[i]) if r >= 0}
+        kth = min(ref.values()) if len(ref) == k else 0.1
+        for row, (fu, _, _) in truth.items():                       # fp32 reference list == oracle on planted rows
+            if fu > kth + FP32_TOL:
+                assert row in ref, (i, row, fu, kth)
+            if row in ref:
+                assert abs(ref[row] - fu) <= FP32_TOL, (i, row, ref[row], fu)
+                oracle_rows += 1
+        got = {int(r): float(s) for r, s in zip(got_i[i], got_f[i]) if r >= 0}
+        hits[i], tot[i] = len(set(got) & set(ref)), len(ref)
+        for row in set(got) & set(ref):
+            want = truth[row][0] if row in truth else ref[row]
+            max_err = max(max_err, abs(got[row] - want))
+    assert oracle_rows >= 0.8 * tot.sum()                           # the top-10s are dominated by oracle-scored rows
+    assert max_err <= BF16_TOL, max_err
+    assert hits.sum() / tot.sum() >= 0.999, hits.sum() / tot.sum()
+    for w in W:
+        sel = np.isclose(wa, w)
+        assert hits[sel].sum() / tot[sel].sum() >= 0.999, (w, hits[sel].sum() / tot[sel].sum())

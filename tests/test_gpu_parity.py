@@ -44,6 +44,26 @@ def test_device_synth_equals_numpy_synth():
     np.testing.assert_array_equal(gfl, f[gi])
 
 
+@pytest.mark.parametrize("mode", ["ascending", "clustered"])
+def test_device_synth_stress_distributions_equal_numpy(mode):
+    """The two stress distributions bench.py measures: device generator == numpy twin, on a shard
+    range in the middle of a 10 M-row global library (row numbers beyond 2^23)."""
+    seed, n, r0, r1 = 20261018, 10_000_000, 9_990_000, 9_992_000
+    a, b, f, _ = synth.library(seed, n, partial=True, r0=r0, r1=r1, mode=mode)
+    idx = SegmentIndex("fp32")
+    idx.append_synth(seed, n, r0, r1, partial=True, mode=mode)
+    np.testing.assert_allclose(idx.read_rows(0, 0, r1 - r0), no.normalize_rows(a), atol=2e-7, rtol=0)
+    np.testing.assert_allclose(idx.read_rows(1, 0, r1 - r0), no.normalize_rows(b), atol=2e-7, rtol=0)
+    np.testing.assert_array_equal(idx.read_flags(), f)
+    q = synth.bench_queries(seed, mode, 0, 2)
+    res = idx.search(q, 0.5, 0.5, k=10)
+    for qi in range(2):
+        o = no.search(q[qi], a, b, f, 0.5, 0.5, k=10)
+        gi, gf, _, _, _ = result_row(res, qi)
+        assert_topk_matches(gi, gf, o, FP32_TOL)
+    idx.close()
+
+
 @pytest.mark.parametrize("dtype,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
 def test_golden_search_cases(search_cases, dtype, tol):
     for case in search_cases:

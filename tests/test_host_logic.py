@@ -48,3 +48,40 @@ def test_synth_plants_are_near_their_query():
             planted += [ca] if kind == 0 else [cb] if kind == 1 else [ca, cb]
         # cosine ~= m/sqrt(m^2+n^2) with m, n in 1..8: spread over (0.12, 0.99)
         assert min(planted) > -0.05 and max(planted) > 0.9 and np.mean(planted) > 0.5
+
+
+def test_synth_row_lists_equal_row_ranges():
+    """`library(rows=[...])` (what bench.py's parity check regenerates) == slices of the range form."""
+    for mode in ("planted", "ascending", "clustered"):
+        a, b, f, _ = synth.library(11, 4000, n_queries=3, plants=9, partial=True, mode=mode)
+        pick = [3999, 0, 17, 2048, 1234]
+        a2, b2, f2, _ = synth.library(11, 4000, n_queries=3, plants=9, partial=True, mode=mode, rows=pick)
+        np.testing.assert_array_equal(a[pick], a2)
+        np.testing.assert_array_equal(b[pick], b2)
+        np.testing.assert_array_equal(f[pick], f2)
+        lo, _, _, _ = synth.library(11, 4000, 3, 9, True, r0=1000, r1=1500, mode=mode)
+        np.testing.assert_array_equal(lo, a[1000:1500])
+
+
+def test_synth_stress_distributions_have_the_advertised_shape():
+    """ascending: for a query near the ascent direction every row scores above its predecessor
+    (the adversarial order for top-k pruning); clustered: a query near a centre has ~N/1024 rows
+    far above the 0.1 threshold and the rest of the library far below them."""
+    n = 200_000
+    unit = lambda x: x / np.linalg.norm(x, axis=-1, keepdims=True)
+    a, b, _, _ = synth.library(3, n, mode="ascending", r0=n - 5000, r1=n)
+    q = unit(synth.bench_queries(3, "ascending", 0, 4))
+    for corpus in (a, b):
+        s = unit(corpus) @ q.T
+        assert (np.diff(s, axis=0) > 0).mean() > 0.99 and s.min() > 0.5
+    rows = np.arange(n)
+    cl = synth.cluster_of_rows(3, rows)
+    assert cl.min() == 0 and cl.max() == synth.N_CLUSTERS - 1
+    q = unit(synth.bench_queries(3, "clustered", 0, 2))
+    for qi in range(2):
+        mine = rows[cl == qi]
+        assert 100 < len(mine) < 320
+        a, b, _, _ = synth.library(3, n, mode="clustered", rows=mine)
+        assert (unit(a) @ q[qi]).min() > 0.45 and (unit(b) @ q[qi]).min() > 0.45
+        a, b, _, _ = synth.library(3, n, mode="clustered", rows=rows[cl != qi][:20000])
+        assert np.abs(unit(a) @ q[qi]).max() < 0.3
