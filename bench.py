@@ -254,7 +254,7 @@ def parity_check(results, queries, wa, wb, k, dtype, n_total, n_plant_queries, p
                 problems.append(f"query {g}: duplicate rows or bad padding")
             for p in range(c):
                 fu, xa, xb = truth[rows[p]]
-                e = max(abs(fus[j, p] - fu), abs(sa[j, p] - xa), abs(sb[j, p] - xb))
+                e = float(max(abs(fus[j, p] - fu), abs(sa[j, p] - xa), abs(sb[j, p] - xb)))
                 max_err = max(max_err, e)
                 if e > tol:
                     problems.append(f"query {g} rank {p} row {rows[p]}: |err| {e:.3g}")
@@ -589,7 +589,7 @@ def main():
             row = int(round(r["start_time"] / 5.0))
             a, b, f, _ = sy.library(SEED, n_rows, n_plant_queries, plants, False, r0=row, r1=row + 1)
             o = no.search(q_host[7], a, b, f, info["asr_weight"], info["audio_weight"], k=1, threshold=-1.0)
-            err = max(err, abs(r["fusion_score"] - float(o.all_fusion[0])))
+            err = float(max(err, abs(r["fusion_score"] - float(o.all_fusion[0]))))
         ok = ok and err <= (1e-5 if dtype == "fp32" else 2e-3)
         idx_rows = len(eng._cab_library.index)
         eng._cab_library.index.close()

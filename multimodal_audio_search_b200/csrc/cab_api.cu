@@ -953,13 +953,28 @@ int cab_score_all(cab_index *idx, const float *queries, int queries_loc, int n_q
     a.chunk_rows = idx->opt_chunk_rows ? int(idx->opt_chunk_rows) : (idx->dtype == CAB_BF16 ? 64 : 32);
     idx->timed = false;
     if (idx->opt_time_kernels) CU(idx, cudaEventRecord(idx->ev_t0, s));
-    for (int q = 0; q < n_queries; ++q) {
-        if (queries_loc == CAB_HOST) { a.use_inline_query = 1; memcpy(a.q, queries + size_t(q) * CAB_DIM, sizeof a.q); }
-        else { a.use_inline_query = 0; a.query = queries + size_t(q) * CAB_DIM; }
-        memcpy(a.class_w, class_weights + size_t(q) * 8, sizeof a.class_w);
+    // Several queries: register-tiled, 4 (then 2, then 1) per corpus pass; host queries are staged once.
+    const float *dq = queries;
+    if (queries_loc == CAB_HOST && n_queries > 1) {
+        const size_t qbytes = size_t(n_queries) * CAB_DIM * sizeof(float);
+        int rc = ensure_dev(idx, &idx->d_params, &idx->sz_params, qbytes);
+        if (rc != CAB_OK) return rc;
+        idx->staged_nq = 0; idx->inline_w_valid = false;            // the parameter block no longer holds search weights
+        CU(idx, cudaMemcpyAsync(idx->d_params, queries, qbytes, cudaMemcpyHostToDevice, s));
+        dq = reinterpret_cast<const float *>(idx->d_params);
+    }
+    a.out_stride = idx->size;
+    for (int q = 0; q < n_queries; ) {
+        const int m = n_queries - q >= 3 ? std::min(4, n_queries - q) : n_queries - q;
+        a.n_q = m;
+        if (queries_loc == CAB_HOST && n_queries == 1) { a.use_inline_query = 1; memcpy(a.q, queries, sizeof a.q); a.query = nullptr; }
+        else { a.use_inline_query = 0; a.query = dq + size_t(q) * CAB_DIM; }
+        memset(a.class_w, 0, sizeof a.class_w);
+        memcpy(a.class_w, class_weights + size_t(q) * 8, size_t(m) * 8 * sizeof(float));
         a.out = d_out + size_t(q) * idx->size;
         launch_score_all(a, idx->sm_count, s);
         idx->launches += 1;
+        q += m;
     }
     if (idx->opt_time_kernels) { CU(idx, cudaEventRecord(idx->ev_t1, s)); idx->timed = true; }
     CU(idx, cudaGetLastError());

@@ -515,11 +515,11 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, E
             const int list = t / k, i = t - list * k;
             const cab_candidate *p = lists + (size_t(list) * nq + qi) * k + i;
             cab_candidate c;                                         // L2 loads: the records were written by peers
-            const longlong2 lo = __ldcg(reinterpret_cast<const longlong2 *>(p));
-            const long long hi = __ldcg(reinterpret_cast<const long long *>(p) + 2);
-            c.index = lo.x;
-            c.asr_sim = __int_as_float(int(uint64_t(lo.y) & 0xFFFFFFFFull)); c.audio_sim = __int_as_float(int(uint64_t(lo.y) >> 32));
-            c.flags = uint32_t(uint64_t(hi) & 0xFFFFFFFFull); c.pad = 0u;
+            const long long *p64 = reinterpret_cast<const long long *>(p);     // 24-byte records: 8-byte aligned
+            const long long w0 = __ldcg(p64), w1 = __ldcg(p64 + 1), w2 = __ldcg(p64 + 2);
+            c.index = w0;
+            c.asr_sim = __int_as_float(int(uint64_t(w1) & 0xFFFFFFFFull)); c.audio_sim = __int_as_float(int(uint64_t(w1) >> 32));
+            c.flags = uint32_t(uint64_t(w2) & 0xFFFFFFFFull); c.pad = 0u;
             return c;
         }, e.n_lists * k, qi, e, !finite, score, index, pos);
         host_signal(e);

@@ -102,11 +102,13 @@ struct ScoreAllArgs {
     const uint8_t *flags;      // bits 2-3 of a row's byte: its weight class
     int64_t n_rows;
     int dtype;
-    const float *query;        // device, raw fp32 [384] (unused when use_inline_query)
-    int use_inline_query;
+    const float *query;        // device, raw fp32 [n_q x 384] (unused when use_inline_query)
+    int n_q;                   // queries scored by this launch (1..4): the corpus is read once for all of them
+    int use_inline_query;      // n_q == 1 only
     float q[CAB_DIM];          // host query, carried in the kernel arguments
-    float class_w[4][2];       // {w_asr, w_audio} per weight class
-    float *out;                // device [n_rows]; all NaN if the query holds NaN/Inf
+    float class_w[4][4][2];    // per query of the launch: {w_asr, w_audio} per weight class
+    float *out;                // device: query t's scores at out + t * out_stride; all NaN if it holds NaN/Inf
+    int64_t out_stride;
     int *nonfinite;            // also set in that case (may be null)
     unsigned int *work_counters;   // [2] chunk tickets + finished warps; zero on entry, re-armed by the kernel
     int chunk_rows;                // rows per dynamically scheduled chunk

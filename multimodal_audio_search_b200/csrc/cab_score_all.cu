@@ -18,6 +18,9 @@
 // same dynamic chunk schedule as the top-k scan; plain butterfly reduction (the issue slots are
 // there: ~60 of ~500 per row are used).  A static warp-cyclic split measured 6-10 % slower
 // (profiles/r01_score_all.md).
+// Several queries per call are register-tiled like the top-k scan (QT = 2 or 4 queries per corpus
+// pass: the rows are loaded once and multiplied with QT query vectors held in registers), so a
+// 32-query legacy call costs 8 HBM passes instead of 32; bit-identical to one query at a time.
 #include "cab_internal.h"
 #include "cab_rowdot.cuh"
 
@@ -28,7 +31,7 @@ constexpr int kScoreWarps = kScoreThreads / 32;
 
 // MB = resident CTAs per SM, part of the register contract with ptxas exactly as in the top-k
 // scan: fp32 U=4 needs 96 registers for the loads in flight alone.
-template <int DT, int U, int MB>
+template <int DT, int U, int MB, int QT>
 __global__ void __launch_bounds__(kScoreThreads, MB)
 score_all_kernel(ScoreAllArgs a) {
     using TR = RowTraits<DT>;
@@ -36,20 +39,25 @@ score_all_kernel(ScoreAllArgs a) {
     constexpr int kRowsPerIter = U * RW;
 
     __shared__ float s_q[kDim];
+    __shared__ float s_cw[QT][4][2];                // class weights: read per row, too many for registers at QT = 4
     if (a.use_inline_query) {
         for (int i = threadIdx.x; i < kDim; i += kScoreThreads) s_q[i] = a.q[i];
-        __syncthreads();
     }
+    if (threadIdx.x < QT * 8) s_cw[threadIdx.x >> 3][(threadIdx.x >> 1) & 3][threadIdx.x & 1] = a.class_w[threadIdx.x >> 3][(threadIdx.x >> 1) & 3][threadIdx.x & 1];
+    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane & (G - 1), sub = lane / G;
 
-    float q[TR::NQ];
-    const float *qsrc = a.query;
-    const bool finite = load_query<DT>([&](int i) { return a.use_inline_query ? s_q[i] : qsrc[i]; }, lane, q);
-    if (!finite && a.nonfinite && blockIdx.x == 0 && threadIdx.x == 0) *a.nonfinite = 1;
-    float cw[4][2];
+    float q[QT][TR::NQ];
+    bool finite[QT];
+    bool any_bad = false;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) { cw[c][0] = a.class_w[c][0]; cw[c][1] = a.class_w[c][1]; }
+    for (int t = 0; t < QT; ++t) {
+        const float *qsrc = a.query + size_t(t < a.n_q ? t : 0) * kDim;      // pad the tile with query 0, never stored
+        finite[t] = load_query<DT>([&](int i) { return a.use_inline_query ? s_q[i] : qsrc[i]; }, lane, q[t]);
+        any_bad |= !finite[t] && t < a.n_q;
+    }
+    if (any_bad && a.nonfinite && blockIdx.x == 0 && threadIdx.x == 0) *a.nonfinite = 1;
 
     const uint4 *__restrict__ A = reinterpret_cast<const uint4 *>(a.asr);
     const uint4 *__restrict__ B = reinterpret_cast<const uint4 *>(a.audio);
@@ -72,7 +80,9 @@ score_all_kernel(ScoreAllArgs a) {
     int64_t chunk = gwarp;
     unsigned int ticket = 0;
     if (chunk < n_chunks && lane == 0) ticket = atomicAdd(counter, 1u);
-    float keep = 0.f;                                       // this lane's pending score (row cbase + 32j + lane)
+    float keep[QT];                                         // this lane's pending scores (row cbase + 32j + lane)
+#pragma unroll
+    for (int t = 0; t < QT; ++t) keep[t] = 0.f;
     // Which row of a step (kRowsPerIter == 4 rows) this lane carries after the transposing
     // reduction, and the lane that carries row (lane & 3) -- see the reduction below.
     static_assert(kRowsPerIter == 4, "the score hand-over assumes 4 rows per step");
@@ -107,14 +117,17 @@ score_all_kernel(ScoreAllArgs a) {
         // Keep all 6U loads in flight: nothing below may be scheduled between the loads above.
 #pragma unroll
         for (int u = 0; u < U; ++u) { keep_live(ca[u]); keep_live(cb[u]); }
-        float v[U][2];
+        constexpr int NV = 2 * QT;
+        float v[U][NV];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            float sa = 0.f, sb = 0.f;
+        for (int u = 0; u < U; ++u)
 #pragma unroll
-            for (int j = 0; j < 3; ++j) { sa = dot_chunk<DT>(ca[u][j], q, j, sa); sb = dot_chunk<DT>(cb[u][j], q, j, sb); }
-            v[u][0] = sa; v[u][1] = sb;
-        }
+            for (int t = 0; t < QT; ++t) {
+                float sa = 0.f, sb = 0.f;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) { sa = dot_chunk<DT>(ca[u][j], q[t], j, sa); sb = dot_chunk<DT>(cb[u][j], q[t], j, sb); }
+                v[u][2 * t] = sa; v[u][2 * t + 1] = sb;
+            }
         // Transposing reduction (the top-k scan's): each split halves the row-steps a lane carries,
         // 12 shuffles per 4 fp32 rows instead of 40 -- fewer instructions, less power under the cap.
         {
@@ -125,7 +138,7 @@ score_all_kernel(ScoreAllArgs a) {
 #pragma unroll
                 for (int i = 0; i < half; ++i)
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
+                    for (int c = 0; c < NV; ++c) {
                         const float send = upper ? v[i][c] : v[i + half][c];
                         const float kept = upper ? v[i + half][c] : v[i][c];
                         v[i][c] = kept + __shfl_xor_sync(kFull, send, stride);
@@ -135,25 +148,31 @@ score_all_kernel(ScoreAllArgs a) {
 #pragma unroll
             for (; stride > 0; stride >>= 1)
 #pragma unroll
-                for (int c = 0; c < 2; ++c) v[0][c] += __shfl_xor_sync(kFull, v[0][c], stride);
+                for (int c = 0; c < NV; ++c) v[0][c] += __shfl_xor_sync(kFull, v[0][c], stride);
         }
         const uint32_t cls = (fl >> 2) & 3u;
-        // fp32 products and sum rounded separately, as numpy evaluates `wa * s_asr + wb * s_cap`
-        // on float32 scalars (no fused multiply-add)
-        const float wa = (cls & 2u) ? ((cls & 1u) ? cw[3][0] : cw[2][0]) : ((cls & 1u) ? cw[1][0] : cw[0][0]);
-        const float wb = (cls & 2u) ? ((cls & 1u) ? cw[3][1] : cw[2][1]) : ((cls & 1u) ? cw[1][1] : cw[0][1]);
-        float f = __fadd_rn(__fmul_rn(wa, v[0][0]), __fmul_rn(wb, v[0][1]));
-        if (!finite) f = __int_as_float(0x7fc00000);      // NaN/Inf query: every score is NaN
-        // Lane (r & 31) keeps the score of the chunk's r-th row, so 32 rows leave as ONE coalesced
-        // 128-byte store (full sectors): the step's row (lane & 3) sits in lane src_lane.
-        const float mine = __shfl_sync(kFull, f, src_lane);
-        if ((((base - cbase) >> 2) & 7) == (lane >> 2)) keep = mine;
+        const bool mine_now = (((base - cbase) >> 2) & 7) == (lane >> 2);
+#pragma unroll
+        for (int t = 0; t < QT; ++t) {
+            // fp32 products and sum rounded separately, as numpy evaluates `wa * s_asr + wb * s_cap`
+            // on float32 scalars (no fused multiply-add)
+            float f = __fadd_rn(__fmul_rn(s_cw[t][cls][0], v[0][2 * t]), __fmul_rn(s_cw[t][cls][1], v[0][2 * t + 1]));
+            if (!finite[t]) f = __int_as_float(0x7fc00000);      // NaN/Inf query: every score is NaN
+            // Lane (r & 31) keeps the score of the chunk's r-th row, so 32 rows leave as ONE coalesced
+            // 128-byte store (full sectors): the step's row (lane & 3) sits in lane src_lane.
+            const float mine = __shfl_sync(kFull, f, src_lane);
+            if (mine_now) keep[t] = mine;
+        }
         const int64_t done = base + kRowsPerIter;                    // rows of this chunk scored so far end here
         const int64_t lim = cend < n ? cend : n;
         if (((done - cbase) & 31) == 0 || done >= lim) {
             const int64_t sbase = cbase + ((done - 1 - cbase) & ~int64_t(31));
             const int64_t row = sbase + lane;
-            if (row < done && row < lim) a.out[row] = keep;
+            if (row < done && row < lim) {
+#pragma unroll
+                for (int t = 0; t < QT; ++t)
+                    if (t < a.n_q) a.out[int64_t(t) * a.out_stride + row] = keep[t];
+            }
         }
     }
     // The last warp to run out of chunks re-arms the counters for the next launch (every warp's
@@ -167,19 +186,28 @@ score_all_kernel(ScoreAllArgs a) {
     }
 }
 
-template <int DT, int U, int MB>
+template <int DT, int U, int MB, int QT>
 static void launch(const ScoreAllArgs &a, int sm_count, cudaStream_t s) {
     using TR = RowTraits<DT>;
     const int64_t rows_per_cta = int64_t(kScoreWarps) * U * TR::RW;
     int64_t grid = (a.n_rows + rows_per_cta - 1) / rows_per_cta;
     if (grid > int64_t(sm_count) * MB) grid = int64_t(sm_count) * MB;   // persistent: every SM full, once
     if (grid < 1) grid = 1;
-    score_all_kernel<DT, U, MB><<<int(grid), kScoreThreads, 0, s>>>(a);
+    score_all_kernel<DT, U, MB, QT><<<int(grid), kScoreThreads, 0, s>>>(a);
 }
 
+// a.n_q queries per pass: 1, 2 or 3..4 (a tile of 4, the unused slots padded and not stored)
 void launch_score_all(const ScoreAllArgs &a, int sm_count, cudaStream_t s) {
-    if (a.dtype == CAB_BF16) launch<CAB_BF16, 2, 2>(a, sm_count, s);
-    else launch<CAB_F32, 4, 1>(a, sm_count, s);
+    const int qt = a.n_q >= 3 ? 4 : a.n_q;
+    if (a.dtype == CAB_BF16) {
+        if (qt == 4) launch<CAB_BF16, 2, 1, 4>(a, sm_count, s);
+        else if (qt == 2) launch<CAB_BF16, 2, 1, 2>(a, sm_count, s);
+        else launch<CAB_BF16, 2, 2, 1>(a, sm_count, s);
+    } else {
+        if (qt == 4) launch<CAB_F32, 4, 1, 4>(a, sm_count, s);
+        else if (qt == 2) launch<CAB_F32, 4, 1, 2>(a, sm_count, s);
+        else launch<CAB_F32, 4, 1, 1>(a, sm_count, s);
+    }
 }
 
 }  // namespace cab

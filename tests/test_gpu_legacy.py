@@ -204,3 +204,35 @@ def test_drop_in_for_clean_audio_search(dtype):
     idx, sims = no.clean_search(q[0], a, ha)
     got = patched.search_audio("x", "asr")
     assert [int(r["segment_id"][4:]) for r in got] == idx.tolist() and [r["similarity"] for r in got] == sims.tolist()
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_query_tiles_are_bit_identical_to_one_query_at_a_time(dtype):
+    """Several queries per call share one corpus pass (register tiles of 4 / 2 / 1 queries): every
+    score must be BIT-identical to the same query scored alone, host and device queries, per-query
+    class weights, and a NaN query must poison only its own row of the result."""
+    import torch
+    rng = np.random.default_rng(5)
+    n, nq = 70_001, 11                                   # tiles: 4 + 4 + 3 (padded tile of 4)
+    a = rng.standard_normal((n, 384)).astype(np.float32)
+    b = rng.standard_normal((n, 384)).astype(np.float32)
+    flags = (3 | (rng.integers(0, 4, n).astype(np.uint8) << 2)).astype(np.uint8)
+    q = rng.standard_normal((nq, 384)).astype(np.float32)
+    cw = rng.uniform(-1, 1, (nq, 4, 2)).astype(np.float32)
+    idx = SegmentIndex(dtype, device=0)
+    idx.append(a, b, flags)
+    alone = np.stack([idx.score_all(q[i], cw[i])[0] for i in range(nq)])
+    for m in (2, 3, 4, 5, 11):
+        got = idx.score_all(q[:m], cw[:m])
+        assert np.array_equal(got, alone[:m]), m
+        dev = idx.score_all(torch.from_numpy(q[:m]).cuda(), cw[:m]).cpu().numpy()
+        assert np.array_equal(dev, alone[:m]), m
+    bad = q[:6].copy()
+    bad[4, 100] = np.inf
+    dev = idx.score_all(torch.from_numpy(bad).cuda(), cw[:6]).cpu().numpy()
+    assert np.isnan(dev[4]).all()
+    assert np.array_equal(np.delete(dev, 4, axis=0), np.delete(alone[:6], 4, axis=0))
+    with pytest.raises(ValueError):
+        idx.score_all(bad, cw[:6])
+    assert np.array_equal(idx.score_all(q[:6], cw[:6]), alone[:6])       # nothing sticky
+    idx.close()
