@@ -125,8 +125,9 @@ CAB_API int cab_index_read_flags(cab_index *idx, int64_t r0, int64_t r1, uint8_t
  * in the Streamlit session, audio_search.py:708-711, and loses it when the session ends) ---------
  * Layout (little endian): 4096-byte header {magic "CABIDX01", version, dim, dtype, n_rows,
  * row_base, section offsets}, then the ASR rows, the audio rows (exactly as resident in HBM:
- * L2-normalised fp32/bf16, row-major) and the flag bytes, each section 4096-byte aligned so the
- * file can be mmap-ed.  A reload is bit-identical: rows are not re-normalised.  Segment metadata
+ * L2-normalised fp32/bf16, row-major), the flag bytes and (version 2) the fp32 original lengths
+ * of the ASR and audio rows, each section 4096-byte aligned so the file can be mmap-ed.
+ * Version-1 files (no lengths) still load; their rows count as unit length.  A reload is bit-identical: rows are not re-normalised.  Segment metadata
  * (texts, times, audio) stays with the caller. */
 CAB_API int cab_index_save(cab_index *idx, const char *path);
 /* Load rows [r0, r1) of a file into a new index on `device` (r1 < 0: to the end).  The new
@@ -230,6 +231,11 @@ CAB_API int cab_index_exchange_stamps(cab_index *idx, uint64_t *out, int max_row
  * "gemv_blocks_per_sm" (resident CTAs per SM, 0 = default), "gemv_query_tile" (queries scored per
  * corpus pass, 1/2/4, 0 = default 4), "gemv_batch", "gemm_min_queries",
  * "time_kernels", "sync_after_search", "stamp_exchange";
+ * "raw_dot" = 1: similarities are raw dot products <query, row> of the vectors AS APPENDED instead
+ * of cosines (the index keeps every row's original length; the query is not normalised) -- the
+ * ranking rule of the reference's earlier engine, previous_iterations/clean_audio_search.py:306-310
+ * (`float(np.dot(query_embedding, embedding))`), for embeddings that are not unit length.  Served
+ * by the GEMV path; threshold, fusion and order are unchanged.  Ignored by cab_score_all.
  * "queries_settled" = 1: the caller promises that DEVICE query buffers passed to a search were
  * completely written before the previous search on this handle was issued (pre-computed query
  * batches); the scan of search i+1 then streams the corpus while search i's finalize / exchange /

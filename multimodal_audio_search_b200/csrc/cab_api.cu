@@ -37,6 +37,7 @@ struct cab_index {
     int sm_count = 148;
     int64_t capacity = 0, size = 0, row_base = 0;
     void *asr = nullptr, *audio = nullptr;
+    float *norm_asr = nullptr, *norm_audio = nullptr;   // original row lengths (raw dot-product scoring)
     uint8_t *flags = nullptr;
     cudaStream_t own_stream = nullptr;
     // search workspace (device)
@@ -65,7 +66,7 @@ struct cab_index {
     // options
     GemvConfig gemv{0, 0, 0, 0};
     int64_t opt_time_kernels = 0, opt_sync = 0, opt_gemm_min_queries = 64, opt_gemv_batch = 32;
-    int64_t opt_queries_settled = 0, opt_stamp_exchange = 0;
+    int64_t opt_queries_settled = 0, opt_stamp_exchange = 0, opt_raw_dot = 0;
     int64_t opt_finalize_general = 0, opt_chunk_rows = 0;    // 0 = auto: 96 KB of corpus per chunk (fp32 32 rows, bf16 64), profiles/r01_gemv_chunk_sweep.md
     // peer-memory exchange (sharded search)
     int peer_world = 0, peer_rank = 0, peer_qcap = 0, peer_kcap = 0;
@@ -140,23 +141,28 @@ static int grow(cab_index *idx, int64_t new_cap) {
     if (new_cap <= idx->capacity) return CAB_OK;
     const size_t row_bytes = CAB_DIM * elem_size(idx->dtype);
     void *na = nullptr, *nb = nullptr;
+    float *la = nullptr, *lb = nullptr;
     uint8_t *nf = nullptr;
     CU(idx, cudaSetDevice(idx->device));
     cudaError_t e = cudaMalloc(&na, size_t(new_cap) * row_bytes);
     if (e == cudaSuccess) e = cudaMalloc(&nb, size_t(new_cap) * row_bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&la, size_t(new_cap) * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&lb, size_t(new_cap) * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&nf, align_up(size_t(new_cap), 16));     // the tensor-core epilogue reads flag WORDS
     if (e != cudaSuccess) {
-        cudaFree(na); cudaFree(nb); cudaFree(nf); cudaGetLastError();
+        cudaFree(na); cudaFree(nb); cudaFree(nf); cudaFree(la); cudaFree(lb); cudaGetLastError();
         return fail(idx, CAB_ERR_NOMEM, "cannot allocate %lld rows (%s)", (long long)new_cap, cudaGetErrorString(e));
     }
     if (idx->size > 0) {
         CU(idx, cudaMemcpyAsync(na, idx->asr, size_t(idx->size) * row_bytes, cudaMemcpyDeviceToDevice, idx->own_stream));
         CU(idx, cudaMemcpyAsync(nb, idx->audio, size_t(idx->size) * row_bytes, cudaMemcpyDeviceToDevice, idx->own_stream));
         CU(idx, cudaMemcpyAsync(nf, idx->flags, size_t(idx->size), cudaMemcpyDeviceToDevice, idx->own_stream));
+        CU(idx, cudaMemcpyAsync(la, idx->norm_asr, size_t(idx->size) * sizeof(float), cudaMemcpyDeviceToDevice, idx->own_stream));
+        CU(idx, cudaMemcpyAsync(lb, idx->norm_audio, size_t(idx->size) * sizeof(float), cudaMemcpyDeviceToDevice, idx->own_stream));
     }
     CU(idx, cudaStreamSynchronize(idx->own_stream));
-    cudaFree(idx->asr); cudaFree(idx->audio); cudaFree(idx->flags);
-    idx->asr = na; idx->audio = nb; idx->flags = nf; idx->capacity = new_cap;
+    cudaFree(idx->asr); cudaFree(idx->audio); cudaFree(idx->flags); cudaFree(idx->norm_asr); cudaFree(idx->norm_audio);
+    idx->asr = na; idx->audio = nb; idx->flags = nf; idx->norm_asr = la; idx->norm_audio = lb; idx->capacity = new_cap;
     return CAB_OK;
 }
 
@@ -206,7 +212,7 @@ int cab_index_destroy(cab_index *idx) {
     if (!idx) return CAB_OK;
     cudaSetDevice(idx->device);
     if (idx->own_stream) cudaStreamSynchronize(idx->own_stream);
-    cudaFree(idx->asr); cudaFree(idx->audio); cudaFree(idx->flags);
+    cudaFree(idx->asr); cudaFree(idx->audio); cudaFree(idx->flags); cudaFree(idx->norm_asr); cudaFree(idx->norm_audio);
     cudaFree(idx->d_params);
     cudaFree(idx->d_partial_keys); cudaFree(idx->d_cands);
     cudaFree(idx->d_out); cudaFree(idx->d_gemm_ws); cudaFree(idx->d_nonfinite); cudaFree(idx->d_rows); cudaFree(idx->d_counters); cudaFree(idx->d_scores);
@@ -277,8 +283,8 @@ int cab_index_append(cab_index *idx, const float *asr_rows, const float *audio_r
     }
     const int64_t dst0 = idx->size;
     if (rows_loc == CAB_DEVICE) {
-        launch_normalize_rows(asr_rows, idx->asr, idx->dtype, dst0, n_rows, idx->d_nonfinite, s);
-        launch_normalize_rows(audio_rows, idx->audio, idx->dtype, dst0, n_rows, idx->d_nonfinite, s);
+        launch_normalize_rows(asr_rows, idx->asr, idx->dtype, dst0, n_rows, idx->d_nonfinite, idx->norm_asr, s);
+        launch_normalize_rows(audio_rows, idx->audio, idx->dtype, dst0, n_rows, idx->d_nonfinite, idx->norm_audio, s);
         idx->launches += 2;
         if (flags) CU(idx, cudaMemcpyAsync(idx->flags + dst0, flags, size_t(n_rows), cudaMemcpyDeviceToDevice, s));
         else CU(idx, cudaMemsetAsync(idx->flags + dst0, 3, size_t(n_rows), s));
@@ -306,8 +312,8 @@ int cab_index_append(cab_index *idx, const float *asr_rows, const float *audio_r
             if (step >= 2) CU(idx, cudaEventSynchronize(idx->ev_slot[slot]));     // the slot's previous chunk is consumed
             if (asr_rows) { memcpy(ha, asr_rows + r * CAB_DIM, size_t(m) * row_bytes); CU(idx, cudaMemcpyAsync(da, ha, size_t(m) * row_bytes, cudaMemcpyHostToDevice, s)); }
             if (audio_rows) { memcpy(hb, audio_rows + r * CAB_DIM, size_t(m) * row_bytes); CU(idx, cudaMemcpyAsync(db, hb, size_t(m) * row_bytes, cudaMemcpyHostToDevice, s)); }
-            launch_normalize_rows(asr_rows ? da : nullptr, idx->asr, idx->dtype, dst0 + r, m, idx->d_nonfinite, s);
-            launch_normalize_rows(audio_rows ? db : nullptr, idx->audio, idx->dtype, dst0 + r, m, idx->d_nonfinite, s);
+            launch_normalize_rows(asr_rows ? da : nullptr, idx->asr, idx->dtype, dst0 + r, m, idx->d_nonfinite, idx->norm_asr, s);
+            launch_normalize_rows(audio_rows ? db : nullptr, idx->audio, idx->dtype, dst0 + r, m, idx->d_nonfinite, idx->norm_audio, s);
             idx->launches += 2;
             CU(idx, cudaEventRecord(idx->ev_slot[slot], s));
         }
@@ -383,7 +389,7 @@ int cab_index_append_synth(cab_index *idx, uint32_t seed, int64_t n_total, int64
         for (int64_t r = 0; r < n_rows; r += chunk) {
             const int64_t m = std::min(chunk, n_rows - r);
             launch_synth_rows(p, st, partial ? 1 : 0, r0 + r, m, idx->d_rows, s);
-            launch_normalize_rows(idx->d_rows, dst, idx->dtype, idx->size + r, m, idx->d_nonfinite, s);
+            launch_normalize_rows(idx->d_rows, dst, idx->dtype, idx->size + r, m, idx->d_nonfinite, st == 0 ? idx->norm_asr : idx->norm_audio, s);
             idx->launches += 2;
         }
     }
@@ -463,6 +469,7 @@ struct FileHeader {
     char magic[8];
     uint32_t version, dim, dtype, reserved;
     uint64_t n_rows, row_base, off_asr, off_audio, off_flags, file_bytes;
+    uint64_t off_norm_asr, off_norm_audio;      // version 2: fp32 original row lengths (raw dot-product scoring)
 };
 constexpr char kMagic[8] = {'C', 'A', 'B', 'I', 'D', 'X', '0', '1'};
 constexpr size_t kFileAlign = 4096;
@@ -476,10 +483,14 @@ int read_header(const char *path, FILE **fp, FileHeader *h, cab_index *idx) {
     if (fread(raw, 1, kFileAlign, f) != kFileAlign) { fclose(f); return fail(idx, CAB_ERR_INVALID, "'%s': truncated header", path); }
     memcpy(h, raw, sizeof(FileHeader));
     const size_t eb = h->dtype == CAB_BF16 ? 2 : 4;
-    bool ok = memcmp(h->magic, kMagic, 8) == 0 && h->version == 1 && h->dim == CAB_DIM &&
+    bool ok = memcmp(h->magic, kMagic, 8) == 0 && (h->version == 1 || h->version == 2) && h->dim == CAB_DIM &&
               (h->dtype == CAB_F32 || h->dtype == CAB_BF16) && h->n_rows <= 0xFFFFFFF0ull &&
               h->off_asr == kFileAlign && h->off_audio >= h->off_asr + h->n_rows * CAB_DIM * eb &&
               h->off_flags >= h->off_audio + h->n_rows * CAB_DIM * eb && h->file_bytes >= h->off_flags + h->n_rows;
+    if (ok && h->version == 2)
+        ok = h->off_norm_asr >= h->off_flags + h->n_rows && h->off_norm_audio >= h->off_norm_asr + h->n_rows * 4 &&
+             h->file_bytes >= h->off_norm_audio + h->n_rows * 4;
+    if (ok && h->version == 1) h->off_norm_asr = h->off_norm_audio = 0;
     if (ok) {
         fseek(f, 0, SEEK_END);
         ok = uint64_t(ftell(f)) >= h->file_bytes;
@@ -511,11 +522,13 @@ int cab_index_save(cab_index *idx, const char *path) {
     const uint64_t n = uint64_t(idx->size);
     FileHeader h{};
     memcpy(h.magic, kMagic, 8);
-    h.version = 1; h.dim = CAB_DIM; h.dtype = uint32_t(idx->dtype); h.n_rows = n; h.row_base = uint64_t(idx->row_base);
+    h.version = 2; h.dim = CAB_DIM; h.dtype = uint32_t(idx->dtype); h.n_rows = n; h.row_base = uint64_t(idx->row_base);
     h.off_asr = kFileAlign;
     h.off_audio = align_up(h.off_asr + n * row_bytes, kFileAlign);
     h.off_flags = align_up(h.off_audio + n * row_bytes, kFileAlign);
-    h.file_bytes = align_up(h.off_flags + n, kFileAlign);
+    h.off_norm_asr = align_up(h.off_flags + n, kFileAlign);
+    h.off_norm_audio = align_up(h.off_norm_asr + n * 4, kFileAlign);
+    h.file_bytes = align_up(h.off_norm_audio + n * 4, kFileAlign);
     int rc = ensure_pinned(idx, &idx->h_rows, &idx->h_rows_bytes, kIoChunk);
     if (rc != CAB_OK) return rc;
     FILE *f = fopen(path, "wb");
@@ -524,10 +537,11 @@ int cab_index_save(cab_index *idx, const char *path) {
     memcpy(zeros.data(), &h, sizeof h);
     bool ok = fwrite(zeros.data(), 1, kFileAlign, f) == kFileAlign;
     memset(zeros.data(), 0, kFileAlign);
-    const struct { const void *src; uint64_t off, bytes; } sect[3] = {
-        {idx->asr, h.off_asr, n * row_bytes}, {idx->audio, h.off_audio, n * row_bytes}, {idx->flags, h.off_flags, n}};
+    const struct { const void *src; uint64_t off, bytes; } sect[5] = {
+        {idx->asr, h.off_asr, n * row_bytes}, {idx->audio, h.off_audio, n * row_bytes}, {idx->flags, h.off_flags, n},
+        {idx->norm_asr, h.off_norm_asr, n * 4}, {idx->norm_audio, h.off_norm_audio, n * 4}};
     uint64_t pos = kFileAlign;
-    for (int s3 = 0; s3 < 3 && ok; ++s3) {
+    for (int s3 = 0; s3 < 5 && ok; ++s3) {
         for (; pos < sect[s3].off && ok; ) { size_t m = std::min<uint64_t>(kFileAlign, sect[s3].off - pos); ok = fwrite(zeros.data(), 1, m, f) == m; pos += m; }
         for (uint64_t done = 0; done < sect[s3].bytes && ok; ) {
             const size_t m = size_t(std::min<uint64_t>(kIoChunk, sect[s3].bytes - done));
@@ -559,11 +573,24 @@ int cab_index_load(const char *path, int device, int64_t r0, int64_t r1, cab_ind
     const size_t row_bytes = CAB_DIM * elem_size(idx->dtype);
     const uint64_t n = uint64_t(r1 - r0);
     rc = ensure_pinned(idx, &idx->h_rows, &idx->h_rows_bytes, kIoChunk);
-    const struct { void *dst; uint64_t off, bytes; } sect[3] = {
+    const struct { void *dst; uint64_t off, bytes; } sect[5] = {
         {idx->asr, h.off_asr + uint64_t(r0) * row_bytes, n * row_bytes},
         {idx->audio, h.off_audio + uint64_t(r0) * row_bytes, n * row_bytes},
-        {idx->flags, h.off_flags + uint64_t(r0), n}};
-    for (int s3 = 0; s3 < 3 && rc == CAB_OK; ++s3) {
+        {idx->flags, h.off_flags + uint64_t(r0), n},
+        {idx->norm_asr, h.off_norm_asr + uint64_t(r0) * 4, n * 4},
+        {idx->norm_audio, h.off_norm_audio + uint64_t(r0) * 4, n * 4}};
+    const int n_sect = h.version >= 2 ? 5 : 3;
+    if (rc == CAB_OK && h.version < 2 && n > 0) {
+        // version-1 file: the original row lengths were not recorded; its rows are served as unit length
+        std::vector<float> ones(size_t(std::min<uint64_t>(n, 1u << 20)), 1.0f);
+        for (uint64_t done = 0; done < n && rc == CAB_OK; done += ones.size()) {
+            const size_t m = size_t(std::min<uint64_t>(ones.size(), n - done));
+            cudaError_t e = cudaMemcpy(idx->norm_asr + done, ones.data(), m * 4, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(idx->norm_audio + done, ones.data(), m * 4, cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) rc = fail(nullptr, CAB_ERR_CUDA, "load: %s", cudaGetErrorString(e));
+        }
+    }
+    for (int s3 = 0; s3 < n_sect && rc == CAB_OK; ++s3) {
         if (fseek(f, long(sect[s3].off), SEEK_SET) != 0) { rc = fail(nullptr, CAB_ERR_INVALID, "seek in '%s' failed", path); break; }
         for (uint64_t done = 0; done < sect[s3].bytes; ) {
             const size_t m = size_t(std::min<uint64_t>(kIoChunk, sect[s3].bytes - done));
@@ -722,10 +749,11 @@ static int run_local(cab_index *idx, const float *queries, int queries_loc, cons
     bool use_gemm = false;
     if (path == CAB_PATH_GEMM) {
         if (idx->dtype != CAB_BF16) return fail(idx, CAB_ERR_INVALID, "the tensor-core path needs a bf16 index");
+        if (idx->opt_raw_dot) return fail(idx, CAB_ERR_INVALID, "raw dot-product scoring (option raw_dot) is served by the GEMV path only");
         if (!gemm_path_available()) return fail(idx, CAB_ERR_INVALID, "tensor-core path not built");
         use_gemm = true;
     } else if (path == CAB_PATH_AUTO) {
-        use_gemm = idx->dtype == CAB_BF16 && nq >= idx->opt_gemm_min_queries && gemm_path_available();
+        use_gemm = idx->dtype == CAB_BF16 && nq >= idx->opt_gemm_min_queries && gemm_path_available() && !idx->opt_raw_dot;
     }
     CU(idx, cudaSetDevice(idx->device));
     const int n_partials = use_gemm ? gemm_partials_per_query(idx->sm_count) : gemv_max_grid(idx->sm_count);
@@ -777,6 +805,7 @@ static int run_local(cab_index *idx, const float *queries, int queries_loc, cons
 
     ScanArgs sa{};
     sa.asr = idx->asr; sa.audio = idx->audio; sa.flags = idx->flags; sa.n_rows = idx->size;
+    if (idx->opt_raw_dot) { sa.norm_asr = idx->norm_asr; sa.norm_audio = idx->norm_audio; }
     sa.dtype = idx->dtype; sa.k = k;
     sa.select_threshold = float(threshold) - 1e-6f;
     sa.partial_keys = idx->d_partial_keys;
@@ -790,6 +819,7 @@ static int run_local(cab_index *idx, const float *queries, int queries_loc, cons
     FinalizeArgs fa{};
     fa.inl = inl;
     fa.asr = idx->asr; fa.audio = idx->audio; fa.flags = idx->flags; fa.dtype = idx->dtype;
+    fa.norm_asr = sa.norm_asr; fa.norm_audio = sa.norm_audio;
     fa.row_base = idx->row_base; fa.k = k; fa.partial_keys = idx->d_partial_keys;
     fa.n_partials = n_partials; fa.force_general = int(idx->opt_finalize_general);
     fa.slot_stride = use_gemm ? kGemmListCap : k;
@@ -1110,6 +1140,7 @@ int cab_index_set_option(cab_index *idx, const char *key, int64_t value) {
     else if (k == "sync_after_search") idx->opt_sync = value != 0;
     else if (k == "finalize_general") idx->opt_finalize_general = value != 0;
     else if (k == "queries_settled") idx->opt_queries_settled = value != 0;
+    else if (k == "raw_dot") idx->opt_raw_dot = value != 0;
     else if (k == "stamp_exchange") { idx->opt_stamp_exchange = value != 0; idx->stamp_calls = 0; }
     else if (k == "gemv_chunk_rows") { if (value < 0 || value > 4096) return fail(idx, CAB_ERR_INVALID, "gemv_chunk_rows in 0..4096 (0 = auto)"); idx->opt_chunk_rows = value; }
     else if (k == "gemm_min_queries") { if (value < 1) return fail(idx, CAB_ERR_INVALID, "gemm_min_queries >= 1"); idx->opt_gemm_min_queries = value; }
@@ -1128,6 +1159,7 @@ int64_t cab_index_get_option(const cab_index *idx, const char *key) {
     if (k == "sync_after_search") return idx->opt_sync;
     if (k == "finalize_general") return idx->opt_finalize_general;
     if (k == "queries_settled") return idx->opt_queries_settled;
+    if (k == "raw_dot") return idx->opt_raw_dot;
     if (k == "stamp_exchange") return idx->opt_stamp_exchange;
     if (k == "gemv_chunk_rows") return idx->opt_chunk_rows;
     if (k == "gemm_min_queries") return idx->opt_gemm_min_queries;

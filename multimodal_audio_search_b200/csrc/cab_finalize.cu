@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, E
     // ---- re-score the winners: one lane group per row, same operation order as the scan ---------
     float q[TR::NQ];
     const float *qsrc = a.queries + size_t(qi) * kDim;
-    const bool finite = load_query<DT>([&](int i) { return a.inl.use_query ? s_q[i] : qsrc[i]; }, lane, q);
+    const bool finite = load_query<DT>([&](int i) { return a.inl.use_query ? s_q[i] : qsrc[i]; }, lane, q, a.norm_asr != nullptr);
     if (!finite) n_win = 0;                                // NaN/Inf query: no results, reported below
     const int g = lane & (TR::G - 1), sub = lane / TR::G;
     const uint4 *__restrict__ A = reinterpret_cast<const uint4 *>(a.asr);
@@ -488,6 +488,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, E
         }
         sa = group_sum<DT>(sa);
         sb = group_sum<DT>(sb);
+        if (a.norm_asr && have) { sa *= a.norm_asr[row]; sb *= a.norm_audio[row]; }      // raw dot products
         if (g == 0 && i < a.k) {
             cab_candidate c;
             c.index = have ? a.row_base + int64_t(row) : (finite ? int64_t(-1) : kBadQueryIndex);

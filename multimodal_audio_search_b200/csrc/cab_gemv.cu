@@ -66,7 +66,7 @@ cab_scan_kernel(ScanArgs a) {
         const int qi = valid ? q0 + t : q0;       // pad the group with its first query, never pushed
         const float *qsrc = a.queries + size_t(qi) * kDim;
         // a NaN/Inf query scores NaN everywhere and selects nothing; the finalize kernel reports it
-        load_query<DT>([&](int i) { return a.inl.use_query ? s_q[i] : qsrc[i]; }, lane, q[t]);
+        load_query<DT>([&](int i) { return a.inl.use_query ? s_q[i] : qsrc[i]; }, lane, q[t], a.norm_asr != nullptr);
         w[t] = a.inl.use_weights ? ScanWeights{a.inl.wa32, a.inl.wb32} : ScanWeights{a.wa32[qi], a.wb32[qi]};
         top[t].init(s_keys[warp][t], a.k, valid ? bound_key(a.select_threshold) : ~0ull);
     }
@@ -125,6 +125,8 @@ cab_scan_kernel(ScanArgs a) {
         }
         const int64_t my_row = base + u_lane * RW + sub;
         const uint32_t fl = a.flags[my_row < n ? my_row : n - 1];
+        float len_a = 1.f, len_b = 1.f;                   // raw dot-product scoring: the rows' original lengths
+        if (a.norm_asr) { len_a = a.norm_asr[my_row < n ? my_row : n - 1]; len_b = a.norm_audio[my_row < n ? my_row : n - 1]; }
         // Keep all 6U loads in flight: nothing below may be scheduled between the loads above.
 #pragma unroll
         for (int u = 0; u < U; ++u) { keep_live(ca[u]); keep_live(cb[u]); }
@@ -162,7 +164,7 @@ cab_scan_kernel(ScanArgs a) {
         }
 #pragma unroll
         for (int t = 0; t < QT; ++t) {
-            const float fused = fuse32(v[0][2 * t], v[0][2 * t + 1], fl, w[t]);
+            const float fused = fuse32(v[0][2 * t] * len_a, v[0][2 * t + 1] * len_b, fl, w[t]);
             const uint64_t key = make_key(fused, uint32_t(my_row));
             top[t].push(owner && my_row < n && key > top[t].bound, key, lane);
         }

@@ -13,7 +13,8 @@ template <bool kBf16>
 __global__ void __launch_bounds__(256) normalize_rows_kernel(const float *__restrict__ src,
                                                              void *__restrict__ dst,
                                                              int64_t dst_row, int64_t n,
-                                                             int *__restrict__ nonfinite) {
+                                                             int *__restrict__ nonfinite,
+                                                             float *__restrict__ norms) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
@@ -33,8 +34,9 @@ __global__ void __launch_bounds__(256) normalize_rows_kernel(const float *__rest
         for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(kFull, ss, o);
         if (__any_sync(kFull, bad) || !isfinite(ss)) { if (lane == 0) *nonfinite = 1; }
         float norm = sqrtf(ss);
-        if (norm == 0.f) norm = 1.f;
         const int64_t out_row = dst_row + r;
+        if (lane == 0) norms[out_row] = norm;         // the row's length, for raw dot-product scoring (0 for a missing row)
+        if (norm == 0.f) norm = 1.f;
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
             float4 o4 = make_float4(v[j].x / norm, v[j].y / norm, v[j].z / norm, v[j].w / norm);
@@ -51,14 +53,14 @@ __global__ void __launch_bounds__(256) normalize_rows_kernel(const float *__rest
 }
 
 void launch_normalize_rows(const float *src, void *dst, int dtype, int64_t dst_row, int64_t n,
-                           int *nonfinite, cudaStream_t s) {
+                           int *nonfinite, float *norms, cudaStream_t s) {
     if (n <= 0) return;
     int64_t blocks = (n + 7) / 8;
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (dtype == CAB_BF16)
-        normalize_rows_kernel<true><<<int(blocks), 256, 0, s>>>(src, dst, dst_row, n, nonfinite);
+        normalize_rows_kernel<true><<<int(blocks), 256, 0, s>>>(src, dst, dst_row, n, nonfinite, norms);
     else
-        normalize_rows_kernel<false><<<int(blocks), 256, 0, s>>>(src, dst, dst_row, n, nonfinite);
+        normalize_rows_kernel<false><<<int(blocks), 256, 0, s>>>(src, dst, dst_row, n, nonfinite, norms);
 }
 
 // ---- read back ---------------------------------------------------------------------------------

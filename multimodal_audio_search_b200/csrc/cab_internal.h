@@ -21,8 +21,9 @@ struct PerDeviceOnce {
 // ---- ingest (cab_ingest.cu) --------------------------------------------------------------------
 // Normalise n raw fp32 rows (sklearn `normalize` semantics) into the store at row offset `dst_row`.
 // src == nullptr writes zero rows.  *nonfinite (device int) is set to 1 if any value is NaN/Inf.
+// norms[dst_row + i] receives the length of raw row i (0 for a zero / missing row).
 void launch_normalize_rows(const float *src, void *dst, int dtype, int64_t dst_row, int64_t n,
-                           int *nonfinite, cudaStream_t s);
+                           int *nonfinite, float *norms, cudaStream_t s);
 // Deterministic synthetic rows (synth.py) for global rows [r0, r1) of stream 0/1, raw fp32.
 struct SynthParams {
     uint32_t seed;
@@ -54,6 +55,10 @@ struct ScanArgs {
     const void *asr;           // [n_rows x 384] normalised rows, fp32 or bf16
     const void *audio;
     const uint8_t *flags;      // [n_rows]
+    // Raw dot-product scoring (option "raw_dot"; clean_audio_search.py:306 ranks by np.dot, not by
+    // cosine): non-null = the stored rows' original lengths; a similarity is then
+    // <q_raw, row_hat> * |row| = <q_raw, row> and the query is NOT normalised.  Null = cosine.
+    const float *norm_asr, *norm_audio;
     int64_t n_rows;
     int dtype;
     const float *queries;      // device, raw fp32 [n_queries x 384]
@@ -137,6 +142,7 @@ struct FinalizeArgs {
     const void *asr;
     const void *audio;
     const uint8_t *flags;
+    const float *norm_asr, *norm_audio;   // raw dot-product scoring, see ScanArgs
     int dtype;
     int64_t row_base;          // global index of local row 0
     const float *queries;

@@ -32,8 +32,9 @@ template <> struct RowTraits<CAB_BF16> {
 // zero norm -> 1).  Every warp computes the norm with the same order, so all agree bit-for-bit.
 // Returns false (warp-uniform) if the query holds NaN/Inf.
 // `get(i)` returns raw query element i (global memory, or the kernel-argument copy).
+// raw = true: keep the query unnormalised (raw dot-product scoring).
 template <int DT, typename Get>
-__device__ __forceinline__ bool load_query(Get get, int lane, float (&q)[RowTraits<DT>::NQ]) {
+__device__ __forceinline__ bool load_query(Get get, int lane, float (&q)[RowTraits<DT>::NQ], bool raw = false) {
     using TR = RowTraits<DT>;
     float ss = 0.f;
     bool bad = false;
@@ -47,7 +48,7 @@ __device__ __forceinline__ bool load_query(Get get, int lane, float (&q)[RowTrai
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(kFull, ss, o);
     bad = __any_sync(kFull, bad) || !isfinite(ss);
     float norm = sqrtf(ss);
-    if (norm == 0.f) norm = 1.f;
+    if (norm == 0.f || raw) norm = 1.f;
     const int g = lane & (TR::G - 1);
 #pragma unroll
     for (int j = 0; j < 3; ++j)
