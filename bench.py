@@ -613,25 +613,47 @@ def main():
         q = synth.raw_queries(SEED + 1, 0, nq)
         qd = torch.from_numpy(q).cuda()
         wa = np.array([W_CLASSES[i % len(W_CLASSES)] for i in range(nq)]); wb = 1.0 - wa
-        bad, n = 0, 0
+        # Bit-exact wherever the answer is determined: the scan selects by fp32 fused score, the final
+        # order is float64, so two rows whose scores differ by less than the fp32 tolerance (1e-5,
+        # BASELINE north_star) may swap at the k-th boundary -- a shard keeps its own top-k, so the
+        # sharded search sees a superset of the single index's candidates there.
+        tol = 1e-5
+        exact, within, n, detail = 0, 0, 0, []
         cases = [(i, i + 1, 10) for i in range(8)] + [(8, 9, 100), (0, 40, 10), (9, 10, 10), (0, 40, 100)]
         for lo, hi, kk in cases:
             want = whole.search(q[lo:hi], wa[lo:hi], wb[lo:hi], k=kk)
             got = sh.search(qd[lo:hi], wa[lo:hi], wb[lo:hi], k=kk, to_host=False)
             goth = sh.search(q[lo:hi], wa[lo:hi], wb[lo:hi], k=kk, to_host=True)
-            for g in (got, goth):
+            for variant, g in (("device", got), ("host", goth)):
                 gi = g.indices.cpu().numpy() if hasattr(g.indices, "cpu") else g.indices
                 gf = g.fusion.cpu().numpy() if hasattr(g.fusion, "cpu") else g.fusion
-                bad += int(not (np.array_equal(gi, want.indices) and np.array_equal(gf, want.fusion)))
-                n += hi - lo
-        t = torch.tensor([bad], device="cuda")
+                for j in range(hi - lo):
+                    n += 1
+                    if np.array_equal(gi[j], want.indices[j]) and np.array_equal(gf[j], want.fusion[j]):
+                        exact += 1
+                        within += 1
+                        continue
+                    # same rows above the (k-th score + tol) line, same scores for the rows both hold
+                    a = {int(r): float(f) for r, f in zip(want.indices[j], want.fusion[j]) if r >= 0}
+                    b = {int(r): float(f) for r, f in zip(gi[j], gf[j]) if r >= 0}
+                    kth = max(min(a.values()) if len(a) == kk else 0.1, min(b.values()) if len(b) == kk else 0.1)
+                    ok = all(a[r] == b[r] for r in set(a) & set(b)) and \
+                        {r for r, f in a.items() if f > kth + tol} == {r for r, f in b.items() if f > kth + tol}
+                    within += int(ok)
+                    if len(detail) < 3:
+                        d = sorted(set(a) ^ set(b))
+                        detail.append({"case": [lo, hi, kk], "variant": variant, "query": lo + j, "ok_within_tolerance": bool(ok),
+                                       "rows_only_in_one": d[:4], "their_scores": [a.get(r, b.get(r)) for r in d[:4]], "kth": kth})
+        t = torch.tensor([n - exact, n - within], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         torch.cuda.synchronize()
         dist.barrier()
         whole.close(); part.close()
-        return {"ok": int(t.item()) == 0, "queries": n, "mismatching_calls_over_all_ranks": int(t.item()),
+        return {"ok": int(t[1].item()) == 0, "queries": n, "not_bit_identical_over_all_ranks": int(t[0].item()),
+                "outside_tolerance_over_all_ranks": int(t[1].item()), "tolerance": tol, "examples_rank0": detail,
                 "what": f"{world} x {per} segments: ShardedSearcher ({exchange_state['kind']}) on every rank vs one index "
-                        f"over all rows on the same rank, bit-exact indices and float64 fusion scores, fused and separate merge"}
+                        f"over all rows on the same rank; identical indices and float64 fusion scores except swaps between rows "
+                        f"closer than the fp32 tolerance at the k-th boundary; fused and separate merge, device and host outputs"}
 
     line = measure(args.workload, args.reps, with_cpu=not args.no_cpu_baseline and world == 1, with_dropin=not args.no_dropin)
     if world > 1:

@@ -136,17 +136,8 @@ class UnifiedAudioSearch:
 CLEAN_TOP_K = 10            # clean_audio_search.py:320
 CLEAN_THRESHOLD = 0.1       # :312
 _CLEAN_OVERFETCH = 64       # candidates taken from the GPU before the exact host re-score
-_NORM_TOL = 1e-3
+_CLEAN_MARGIN = 0.01        # the over-fetch threshold sits this far below 0.1 (GPU fp32/bf16 vs the host re-score)
 _CLEAN_KEYS = {"combined": "combined_embedding", "asr": "asr_embedding", "caption": "caption_embedding"}
-
-
-def _unit_row(e, what: str) -> np.ndarray:
-    a = _row(e)
-    norm = float(np.linalg.norm(a.astype(np.float64)))
-    if abs(norm - 1.0) > _NORM_TOL:
-        raise ValueError(f"{what} has length {norm:.4f}: ranking by raw dot product (clean_audio_search.py:306) "
-                         "is served by the cosine scan only for unit-length embeddings (all-MiniLM-L6-v2 produces them)")
-    return a
 
 
 class _CleanDatabase:
@@ -166,6 +157,10 @@ class _CleanDatabase:
             cap = max(1024, len(database))
             self.pair = SegmentIndex(self.dtype, capacity=cap, device=self.device)
             self.combined = SegmentIndex(self.dtype, capacity=cap, device=self.device)
+            # :306 ranks by the RAW dot product: embeddings of any length are served (the index keeps
+            # each row's original length; for unit-length MiniLM rows this is the cosine)
+            self.pair.set_option("raw_dot", 1)
+            self.combined.set_option("raw_dot", 1)
         replaced = database is not self._list or self.n_synced > len(database) or \
             (self.n_synced and database[self.n_synced - 1] is not self._last)
         if replaced:
@@ -180,7 +175,7 @@ class _CleanDatabase:
             for i, seg in enumerate(database[self.n_synced:]):
                 for key in _CLEAN_KEYS.values():
                     if seg.get(key) is not None:
-                        rows[key][i] = _unit_row(seg[key], f"segment {self.n_synced + i} {key}")
+                        rows[key][i] = _row(seg[key])
                         has[key][i] = 1
             self.pair.append(rows["asr_embedding"], rows["caption_embedding"],
                              has["asr_embedding"] | (has["caption_embedding"] << 1))
@@ -198,11 +193,11 @@ def _b200_search_audio(self, query: str, search_mode: str = "combined") -> List[
     key = _CLEAN_KEYS.get(search_mode)
     if key is None:
         return []                                                             # every similarity stays 0.0 (:303-310)
-    q = _unit_row(query_embedding, "the query embedding")
+    q = _row(query_embedding)
     pair, combined = self._cab_database.sync(self.audio_database)
     index, wa, wb = (combined, 1.0, 0.0) if search_mode == "combined" else \
         (pair, 1.0, 0.0) if search_mode == "asr" else (pair, 0.0, 1.0)
-    res = index.search(q[None, :], wa, wb, k=_CLEAN_OVERFETCH, threshold=CLEAN_THRESHOLD - 10 * _NORM_TOL)
+    res = index.search(q[None, :], wa, wb, k=_CLEAN_OVERFETCH, threshold=CLEAN_THRESHOLD - _CLEAN_MARGIN)
     scored = []
     for j in range(int(res.count[0])):
         i = int(res.indices[0, j])

@@ -186,12 +186,25 @@ def test_drop_in_for_clean_audio_search(dtype):
                 assert [r["similarity"] for r in got] == sims.tolist()            # the reference's own floats
             for r in got:
                 assert set(r) == set(db[0]) | {"similarity"} and type(r["similarity"]) is float
-    # non-unit embeddings: raw-dot ranking is not the cosine ranking -> refused, not approximated
-    bad = legacy.CleanAudioSearch(text_embedder=FakeEmbedder({"x": q[0]}))
-    seg = dict(db[0]); seg["combined_embedding"] = 2.0 * seg["combined_embedding"]
-    bad.audio_database.append(seg)
-    with pytest.raises(ValueError, match="unit-length"):
-        bad.search_audio("x", "combined")
+    # non-unit embeddings (and a non-unit query): :306 ranks by the RAW dot product, which is not the
+    # cosine ranking -- served through the index's row lengths, same ids and floats as the oracle
+    rng = np.random.default_rng(3)
+    scale_a = rng.uniform(0.2, 5.0, len(db)).astype(np.float32)
+    scale_c = rng.uniform(0.2, 5.0, len(db)).astype(np.float32)
+    a2, c2, m2 = a * scale_a[:, None], c * scale_c[:, None], m * scale_a[:, None]
+    db2 = clean_database(a2, c2, m2, ha, hc)
+    q2 = (1.7 * q[0]).astype(np.float32)
+    raw = legacy.CleanAudioSearch(dtype=dtype, text_embedder=FakeEmbedder({"x": q2, "y": (0.6 * qm[1]).astype(np.float32)}))
+    raw.audio_database.extend(db2)
+    for text, mode, rows, has, qv in (("x", "asr", a2, ha, q2), ("x", "caption", c2, hc, q2),
+                                      ("y", "combined", m2, everything, (0.6 * qm[1]).astype(np.float32))):
+        idx, sims = no.clean_search(qv, rows, has)
+        cos_idx, _ = no.clean_search(qv / np.linalg.norm(qv), rows / np.maximum(np.linalg.norm(rows, axis=1, keepdims=True), 1e-30), has)
+        got = raw.search_audio(text, mode)
+        assert [int(r["segment_id"][4:]) for r in got] == idx.tolist()
+        assert [r["similarity"] for r in got] == sims.tolist()
+        if mode == "asr":
+            assert idx.tolist() != cos_idx.tolist()                               # the scales really change the ranking
 
     class ReferenceLike:
         def __init__(self):

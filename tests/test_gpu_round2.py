@@ -272,3 +272,48 @@ def test_peer_exchange_two_processes_one_gpu(tmp_path):
                 np.testing.assert_array_equal(z[f"i{rep}_{ci}"], w.indices, err_msg=f"rank {rank} case {ci}")
                 np.testing.assert_array_equal(z[f"f{rep}_{ci}"], w.fusion)
                 np.testing.assert_array_equal(z[f"c{rep}_{ci}"], w.count)
+
+
+@pytest.mark.parametrize("dtype,rel", [("fp32", 2e-6), ("bf16", 4e-3)])
+def test_raw_dot_product_scoring_for_non_unit_embeddings(dtype, rel, tmp_path):
+    """Option "raw_dot": similarities are <query, row> of the vectors as appended (the ranking rule of
+    previous_iterations/clean_audio_search.py:306-310), for rows and queries of any length; fusion,
+    threshold and order unchanged.  The row lengths survive growth of the store and a save / load."""
+    rng = np.random.default_rng(12)
+    n, nq = 50_000, 5
+    a = rng.standard_normal((n, 384)).astype(np.float32) * rng.uniform(0.01, 0.3, (n, 1)).astype(np.float32)
+    b = rng.standard_normal((n, 384)).astype(np.float32) * rng.uniform(0.01, 0.3, (n, 1)).astype(np.float32)
+    f = rng.choice(np.array([1, 2, 3, 3, 3], np.uint8), n)
+    a[(f & 1) == 0] = 0; b[(f & 2) == 0] = 0
+    q = rng.standard_normal((nq, 384)).astype(np.float32) * np.float32(0.7)
+    idx = SegmentIndex(dtype, capacity=1000)                 # grows several times while appending
+    for lo in range(0, n, 7000):
+        idx.append(a[lo:lo + 7000], b[lo:lo + 7000], f[lo:lo + 7000])
+    cos = idx.search(q, 0.4, 0.6, k=20)
+    idx.set_option("raw_dot", 1)
+    res = idx.search(q, 0.4, 0.6, k=20)
+
+    def check(res):
+        for qi in range(nq):
+            sa, sb = a @ q[qi], b @ q[qi]
+            fusion, _, _ = no.fuse(sa, sb, f, 0.4, 0.6)
+            order = np.argsort(-fusion, kind="stable")
+            want = [int(r) for r in order[:20] if fusion[r] > 0.1]
+            gi, gf, ga, gb, _ = result_row(res, qi)
+            tol = rel * max(1.0, float(np.abs(fusion[np.isfinite(fusion)]).max()))
+            assert len(gi) == len(want) or abs(fusion[order[len(gi)]] - 0.1) <= tol
+            for p, r in enumerate(gi.tolist()):
+                assert abs(gf[p] - fusion[r]) <= tol and abs(ga[p] - sa[r]) <= tol and abs(gb[p] - sb[r]) <= tol
+                if p < len(want) and r != want[p]:
+                    assert abs(fusion[r] - fusion[want[p]]) <= tol
+    check(res)
+    assert res.indices.tolist() != cos.indices.tolist()          # not the cosine ranking
+    with pytest.raises(Exception, match="GEMV"):
+        idx.search(np.tile(q, (20, 1))[:70], 0.4, 0.6, k=10, path="gemm")
+    path = str(tmp_path / "raw.idx")
+    idx.save(path)
+    again = SegmentIndex.load(path)
+    again.set_option("raw_dot", 1)
+    r2 = again.search(q, 0.4, 0.6, k=20)
+    assert r2.indices.tolist() == res.indices.tolist() and r2.fusion.tolist() == res.fusion.tolist()
+    idx.close(); again.close()

@@ -141,6 +141,9 @@ class _FakeIndex:
     def clear(self):
         self.a, self.b, self.f = self.a[:0], self.b[:0], self.f[:0]
 
+    def set_option(self, key, value):
+        self.options = getattr(self, "options", {}) | {key: value}      # unit-length rows here: raw dot == cosine
+
     def pinned_scores(self, nq=1):
         return np.empty((nq, len(self)), np.float32)
 
@@ -194,7 +197,9 @@ def test_drop_in_host_logic_with_a_fake_index(monkeypatch):
         got = ceng.search_audio(f"{r['mode']} {r['qi']}", r["mode"])
         assert [int(x["segment_id"][4:]) for x in got] == r["indices"]
         np.testing.assert_allclose([x["similarity"] for x in got], r["similarity"], atol=1e-6, rtol=0)
+    # embeddings of any length are accepted: the engine is told to rank by the raw dot product (:306)
     seg = dict(cdb[0]); seg["asr_embedding"] = 3.0 * cdb[0]["combined_embedding"]
     ceng.audio_database.append(seg)
-    with pytest.raises(ValueError, match="unit-length"):
-        ceng.search_audio("asr 0", "asr")
+    ceng.search_audio("asr 0", "asr")
+    assert ceng._cab_database.pair.options == {"raw_dot": 1} and ceng._cab_database.combined.options == {"raw_dot": 1}
+    assert len(ceng._cab_database.pair) == len(cdb) + 1
