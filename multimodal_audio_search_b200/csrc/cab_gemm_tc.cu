@@ -201,6 +201,13 @@ struct GemmParams {
     // with fused score in [thr + j*kLevelStep, thr + (j+1)*kLevelStep).  If the counts of levels
     // >= j sum to k or more, the global k-th best score is >= thr + j*kLevelStep: a safe bound.
     int32_t *levels;               // [256 queries][kLevels]
+    // Visiting order of the tile rounds (round r = the n_pairs tiles [r * n_pairs, (r+1) * n_pairs)):
+    // the it-th round a pair works on is (it * round_mul) % n_rounds_full, a bijection.  A library
+    // whose scores ascend with the row number -- every row beating the running k-th best, the
+    // adversarial order for the pruning epilogue -- then looks like a random one at round
+    // granularity; the pairs still sweep n_pairs consecutive tiles at a time.
+    uint32_t n_rounds_full;        // rounds in which every pair has a tile
+    uint32_t round_mul;
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
@@ -245,6 +252,11 @@ gemm_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
     const int64_t n_tiles = (p.n_rows + kTileRows - 1) / kTileRows;
+    // tile of this pair's it-th round (>= n_tiles: no more work)
+    auto tile_of = [&](uint32_t it) -> int64_t {
+        const uint32_t r = it < p.n_rounds_full ? uint32_t((uint64_t(it) * p.round_mul) % p.n_rounds_full) : it;
+        return int64_t(r) * p.n_pairs + pair;
+    };
 
     if (warp == 0) {
         // ===== TMA producer (one lane in each CTA): own 128 queries once, then own half of every tile
@@ -254,8 +266,8 @@ gemm_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             for (int kb = 0; kb < kNumKBlocks; ++kb)
                 tma_load_2d_pair(smem_base + kOffQ + kb * kQBlockBytes, &map_q, q_bar_leader, kb * kKBlock,
                                  int(cta_rank) * kQPerCta, kEvictLast);
-            uint32_t n = 0;
-            for (int64_t tile = pair; tile < n_tiles; tile += p.n_pairs) {
+            uint32_t n = 0, rnd = 0;
+            for (int64_t tile = tile_of(0); tile < n_tiles; tile = tile_of(++rnd)) {
                 const int row0 = int(tile * kTileRows) + int(cta_rank) * kHalfRows;
                 for (int kb = 0; kb < kNumKBlocks; ++kb, ++n) {
                     const int s = n % kStages;
@@ -275,7 +287,7 @@ gemm_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             mbar_wait(q_bar, 0, p.status, 2);
             tc_fence_after();
             uint32_t n = 0, it = 0;
-            for (int64_t tile = pair; tile < n_tiles; tile += p.n_pairs, ++it) {
+            for (int64_t tile = tile_of(0); tile < n_tiles; tile = tile_of(++it)) {
                 const uint32_t t = it & 1u, tph = (it >> 1) & 1u;
                 mbar_wait(tmem_empty_bar(t), tph ^ 1u, p.status, 3);
                 tc_fence_after();
@@ -346,12 +358,12 @@ gemm_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         load_levels(0, lv_lo, lv_hi);
 
         uint32_t it = 0;
-        uint32_t flag_word = load_flags(pair);
-        for (int64_t tile = pair; tile < n_tiles; tile += p.n_pairs, ++it) {
+        uint32_t flag_word = load_flags(tile_of(0));
+        for (int64_t tile = tile_of(0); tile < n_tiles; tile = tile_of(++it)) {
             const uint32_t t = it & 1u, tph = (it >> 1) & 1u;
             const uint32_t row0 = uint32_t(tile * kTileRows);
             const uint32_t fw = flag_word;
-            flag_word = load_flags(tile + p.n_pairs);                          // prefetch the next tile's flags
+            flag_word = load_flags(tile_of(it + 1));                           // prefetch the next tile's flags
             const bool fast = thr_nonneg && __all_sync(kFull, (fw & 0x03030303u) == 0x03030303u);   // bits 2-3: weight class, not used here
             {   // refresh the bound of lane (it & 31)'s query from the shared level histogram
                 int s_hi = lv_hi, s_lo = lv_lo;                                // inclusive suffix sums over lanes
@@ -527,6 +539,19 @@ void launch_gemm_scan(const ScanArgs &a, int sm_count, void *workspace, size_t w
     p.flags = a.flags; p.n_rows = a.n_rows; p.wa32 = a.wa32; p.wb32 = a.wb32; p.n_queries = a.n_queries;
     p.k = a.k; p.select_threshold = a.select_threshold; p.lists = a.partial_keys; p.counts = counts;
     p.n_pairs = sm_count / 2; p.status = status; p.levels = levels;
+    {
+        const int64_t n_tiles = (a.n_rows + kTileRows - 1) / kTileRows;
+        const uint64_t full = uint64_t(n_tiles / p.n_pairs);
+        uint64_t mul = 1;
+        if (full > 2) {                                    // ~golden-ratio stride, coprime to the round count
+            mul = uint64_t(double(full) * 0.6180339887) | 1ull;
+            auto gcd = [](uint64_t x, uint64_t y) { while (y) { const uint64_t t = x % y; x = y; y = t; } return x; };
+            while (gcd(mul, full) != 1) mul += 2;
+            mul %= full;
+            if (mul == 0) mul = 1;
+        }
+        p.n_rounds_full = uint32_t(full); p.round_mul = uint32_t(mul);
+    }
 
     // prologue -> scan, both with programmatic stream serialization: the prologue's launch overlaps
     // the previous pass's finalize, the scan's setup (barriers, TMEM, cluster sync) the prologue.

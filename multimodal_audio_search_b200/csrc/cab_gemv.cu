@@ -93,13 +93,20 @@ cab_scan_kernel(ScanArgs a) {
     // per warp, so the tail -- warps finishing at different times while the memory system drains --
     // is a few microseconds instead of one big chunk's worth (the ticket counter is one address:
     // smaller tail chunks or a longer tail region would make the atomics the bottleneck).
-    const int kChunkRows = a.chunk_rows >= kRowsPerIter ? (a.chunk_rows / kRowsPerIter) * kRowsPerIter : kRowsPerIter;
-    const int kSmallRows = kChunkRows / 4 >= kRowsPerIter ? (kChunkRows / 4 / kRowsPerIter) * kRowsPerIter : kRowsPerIter;
-    int64_t n_big = n / kChunkRows - total_warps;              // big chunks handed out before the tail
-    if (n_big < 0) n_big = 0;
-    const int64_t tail_row0 = n_big * kChunkRows;
-    const int64_t n_small = (n - tail_row0 + kSmallRows - 1) / kSmallRows;
-    const int64_t n_chunks = n_big + n_small;
+    // The 64-chunk groups of the bulk are visited in a scattered order (group g at position
+    // (g * super_mul) % n_super, a bijection): a library whose scores ASCEND with the row number
+    // -- the adversarial order for a pruning scan, every row beating the running k-th best -- then
+    // looks like a random one at group granularity (the bound is high after the first few groups
+    // and whole groups are rejected by one compare), while all warps still work inside the same
+    // few megabytes at any time, like the plain sweep.
+    const int kChunkRows = a.rows_big, kSmallRows = a.rows_small;
+    const int64_t n_big = a.n_big, tail_row0 = a.tail_row0, n_chunks = a.n_chunks;
+    const int64_t n_grouped = int64_t(a.n_super) << 6;
+    auto chunk_row0 = [&](int64_t c) -> int64_t {
+        if (c >= n_big) return tail_row0 + (c - n_big) * kSmallRows;
+        if (c < n_grouped) c = (int64_t((uint64_t(c >> 6) * a.super_mul) % a.n_super) << 6) | (c & 63);
+        return c * kChunkRows;
+    };
     unsigned int *counter = a.work_counters + blockIdx.y;
     int64_t chunk = gwarp;
     // The ticket counter was reset by the previous search's finalize kernel before it released its
@@ -110,8 +117,7 @@ cab_scan_kernel(ScanArgs a) {
     for (; chunk < n_chunks;
          chunk = total_warps + int64_t(__shfl_sync(kFull, ticket, 0)),
          ticket = (lane == 0 && chunk < n_chunks) ? atomicAdd(counter, 1u) : 0u)
-    for (int64_t base = chunk < n_big ? chunk * kChunkRows : tail_row0 + (chunk - n_big) * kSmallRows,
-                 cend = chunk < n_big ? base + kChunkRows : base + kSmallRows;
+    for (int64_t base = chunk_row0(chunk), cend = chunk < n_big ? base + kChunkRows : base + kSmallRows;
          base < cend && base < n; base += kRowsPerIter) {
         uint4 ca[U][3], cb[U][3];
 #pragma unroll
@@ -265,7 +271,33 @@ static void launch_dt(const ScanArgs &a, const GemvPlan &p, dim3 grid, cudaStrea
 #undef CAB_CASE
 }
 
-void launch_gemv_scan(const ScanArgs &a, const GemvPlan &p, cudaStream_t s) {
+static uint64_t gcd64(uint64_t a, uint64_t b) { while (b) { const uint64_t t = a % b; a = b; b = t; } return a; }
+
+// Two-level chunk schedule (see the kernel) for `n_rows` rows scanned by `total_warps` warps that
+// each take `rows_per_iter` rows per step; `want_rows` = requested rows per big chunk.
+void gemv_chunk_layout(ScanArgs *a, int want_rows, int rows_per_iter, int64_t total_warps) {
+    a->rows_big = want_rows >= rows_per_iter ? (want_rows / rows_per_iter) * rows_per_iter : rows_per_iter;
+    a->rows_small = a->rows_big / 4 >= rows_per_iter ? (a->rows_big / 4 / rows_per_iter) * rows_per_iter : rows_per_iter;
+    int64_t n_big = a->n_rows / a->rows_big - total_warps;     // big chunks handed out before the tail
+    if (n_big < 0) n_big = 0;
+    a->n_big = n_big;
+    a->tail_row0 = n_big * a->rows_big;
+    a->n_chunks = n_big + (a->n_rows - a->tail_row0 + a->rows_small - 1) / a->rows_small;
+    a->n_super = uint32_t(n_big >> 6);
+    uint64_t mul = 1;
+    if (a->n_super > 2) {                                      // ~golden-ratio stride, coprime to the group count
+        mul = uint64_t(double(a->n_super) * 0.6180339887) | 1ull;
+        while (gcd64(mul, a->n_super) != 1) mul += 2;
+        mul %= a->n_super;
+        if (mul == 0) mul = 1;
+    }
+    a->super_mul = uint32_t(mul);
+}
+
+void launch_gemv_scan(const ScanArgs &a_in, const GemvPlan &p, cudaStream_t s) {
+    ScanArgs a = a_in;
+    const int rw = a.dtype == CAB_BF16 ? RowTraits<CAB_BF16>::RW : RowTraits<CAB_F32>::RW;
+    gemv_chunk_layout(&a, a.chunk_rows, p.u * rw, int64_t(p.grid_x) * kScanWarps);
     dim3 grid(p.grid_x, p.groups);
     if (a.dtype == CAB_BF16) launch_dt<CAB_BF16>(a, p, grid, s);
     else launch_dt<CAB_F32>(a, p, grid, s);

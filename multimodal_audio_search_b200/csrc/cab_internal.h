@@ -73,7 +73,11 @@ struct ScanArgs {
     int32_t *partial_counts;   // GEMM only: [n_queries][n_partials]
     int n_partials;            // == grid size of the scan (GEMV) / number of CTA pairs (GEMM)
     unsigned int *work_counters;   // GEMV: [n_queries] chunk tickets, zero on entry (finalize resets them)
-    int chunk_rows;                // GEMV: rows per dynamically scheduled chunk
+    int chunk_rows;                // GEMV: rows per dynamically scheduled chunk (request; 0 = default)
+    // GEMV chunk schedule, filled in by launch_gemv_scan (see ChunkLayout in cab_gemv.cu)
+    int rows_big, rows_small;      // rows per big / tail chunk
+    int64_t n_big, n_chunks, tail_row0;
+    uint32_t n_super, super_mul;   // visiting order of the 64-chunk groups: group g is read at (g * super_mul) % n_super
     // Where the scan executes griddepcontrol.wait (it is launched with programmatic stream
     // serialization).  1: before its first global read -- the device query / staged weights may have
     // been written by the kernel right in front of it on the caller's stream.  0: only before it
