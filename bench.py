@@ -267,8 +267,11 @@ def parity_check(results, queries, wa, wb, k, dtype, n_total, n_plant_queries, p
             for r in expected:
                 if truth[r][0] > kth + tol and r not in rows:
                     problems.append(f"query {g}: expected row {r} (oracle score {truth[r][0]:.6f}) missing, k-th {kth:.6f}")
-            if mode == "ascending" and (c != k or min(rows) < n_total - k - 64):
-                problems.append(f"query {g}: ascending library, results {sorted(rows)[:3]}.. are not the last rows")
+            # ascending library: the answer is the tail of the library; rows whose scores differ by less
+            # than the tolerance (alpha rises by 0.8 / n_total per row) may swap
+            slack = k + 64 + int(2 * tol * n_total / 0.8)
+            if mode == "ascending" and (c != k or min(rows) < n_total - slack):
+                problems.append(f"query {g}: ascending library, results {sorted(rows)[:3]}.. are not within the last {slack} rows")
             n_q += 1
             n_rows_checked += len(need)
     return {"ok": not problems, "queries": n_q, "rows_scored_by_oracle": n_rows_checked, "max_abs_err": max_err,

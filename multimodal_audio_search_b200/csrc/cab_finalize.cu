@@ -81,6 +81,21 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// A candidate record read from L2 (ld.global.cg), never from L1: exchange buffers are written by
+// peers over NVLink (and by this GPU's earlier kernels) while the reading kernel may already be
+// resident -- it is launched early, by programmatic dependent launch, while its predecessor still
+// runs -- so a line cached in this SM's L1 by the merge of two searches ago would be served stale
+// (seen on two B200s: the merge mixed in the candidates of an earlier call).  24-byte records are
+// 8-byte aligned: three 64-bit loads.
+__device__ __forceinline__ cab_candidate load_candidate_l2(const cab_candidate *p) {
+    const long long *p64 = reinterpret_cast<const long long *>(p);
+    const long long w0 = __ldcg(p64), w1 = __ldcg(p64 + 1), w2 = __ldcg(p64 + 2);
+    cab_candidate c;
+    c.index = w0;
+    c.asr_sim = __int_as_float(int(uint64_t(w1) & 0xFFFFFFFFull)); c.audio_sim = __int_as_float(int(uint64_t(w1) >> 32));
+    c.flags = uint32_t(uint64_t(w2) & 0xFFFFFFFFull); c.pad = uint32_t(uint64_t(w2) >> 32);
+    return c;
+}
 // Slot of candidate i of query q (index within the whole call) of rank `rank` in an exchange buffer.
 __device__ __forceinline__ size_t peer_slot(const PeerPush &p, int q, int k, int i) {
     return (size_t(p.rank) * p.n_queries_total + q) * k + i;
@@ -111,11 +126,15 @@ __device__ __forceinline__ void peer_push_and_signal(const PeerPush &p, const ca
             const unsigned prev = atomicAdd(p.done_counter, 1u);
             *s_last = prev == gridDim.x - 1;
             if (*s_last) *p.done_counter = 0u;
+            __threadfence();                      // acquire side: the other CTAs' (fenced) stores precede their count
         }
         __syncthreads();
         if (!*s_last) return;
     }
-    if (threadIdx.x < p.world) st_release_sys(p.flags[threadIdx.x] + p.parity * p.world + p.rank, p.epoch);
+    if (threadIdx.x < p.world) {
+        __threadfence_system();
+        st_release_sys(p.flags[threadIdx.x] + p.parity * p.world + p.rank, p.epoch);
+    }
 }
 
 // Host-visible completion of a launch whose outputs live in mapped pinned host memory: called by
@@ -514,14 +533,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, E
         const int nq = e.n_queries, k = e.k;
         emit_ranked([&](int t) {
             const int list = t / k, i = t - list * k;
-            const cab_candidate *p = lists + (size_t(list) * nq + qi) * k + i;
-            cab_candidate c;                                         // L2 loads: the records were written by peers
-            const long long *p64 = reinterpret_cast<const long long *>(p);     // 24-byte records: 8-byte aligned
-            const long long w0 = __ldcg(p64), w1 = __ldcg(p64 + 1), w2 = __ldcg(p64 + 2);
-            c.index = w0;
-            c.asr_sim = __int_as_float(int(uint64_t(w1) & 0xFFFFFFFFull)); c.audio_sim = __int_as_float(int(uint64_t(w1) >> 32));
-            c.flags = uint32_t(uint64_t(w2) & 0xFFFFFFFFull); c.pad = 0u;
-            return c;
+            return load_candidate_l2(lists + (size_t(list) * nq + qi) * k + i);
         }, e.n_lists * k, qi, e, !finite, score, index, pos);
         host_signal(e);
         if (stamp) e.stamps[3] = globaltimer_ns();
@@ -563,7 +575,7 @@ __global__ void __launch_bounds__(kEmitMax) emit_kernel(EmitArgs a) {
     const cab_candidate *lists = a.cands;
     emit_ranked([&](int t) {
         const int list = t / k, i = t - list * k;
-        return lists[(size_t(list) * nq + qi) * k + i];
+        return load_candidate_l2(lists + (size_t(list) * nq + qi) * k + i);
     }, a.n_lists * k, qi, a, false, s_score, s_index, s_pos);
     host_signal(a);
 }

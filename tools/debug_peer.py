@@ -5,27 +5,33 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
-def worker(rank, world, port):
+def worker(rank, world, port, two_gpus):
     import torch, torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from multimodal_audio_search_b200 import SegmentIndex, ShardedSearcher, synth
     from oracle import numpy_oracle as no
-    torch.cuda.set_device(0)
+    dev = rank if two_gpus else 0
+    torch.cuda.set_device(dev)
     SEED, per, nq = 20261019, 60_000, 40
     n_total = per * world
-    whole = SegmentIndex("fp32", capacity=n_total)
+    whole = SegmentIndex("fp32", capacity=n_total, device=dev)
     whole.append_synth(SEED, n_total, 0, n_total, n_queries=nq, plants=30, partial=True)
-    part = SegmentIndex("fp32", capacity=per)
+    part = SegmentIndex("fp32", capacity=per, device=dev)
     part.append_synth(SEED, n_total, rank * per, (rank + 1) * per, n_queries=nq, plants=30, partial=True)
     part.row_base = rank * per
     sh = ShardedSearcher(part, rank, world, exchange="p2p", max_queries=64, max_k=100)
     q = synth.raw_queries(SEED, 0, nq)
     wa = np.array([[0.5, 0.2, 0.3, 0.4, 0.6, 0.7, 0.8][i % 7] for i in range(nq)]); wb = 1 - wa
     a, b, f, _ = synth.library(SEED, n_total, nq, 30, True)
-    for lo, hi, kk in ((0, 40, 100), (0, 33, 100), (0, 32, 100), (0, 40, 50), (0, 40, 64), (0, 40, 65)):
+    qd = torch.from_numpy(q).cuda()
+    seq = [(i, i + 1, 10) for i in range(8)] + [(8, 9, 100), (0, 40, 10), (9, 10, 10), (0, 40, 100)] if os.environ.get("BENCH_SEQ") else []
+    for lo, hi, kk in seq + [(0, 40, 100), (0, 33, 100), (0, 32, 100), (0, 40, 50), (0, 40, 64), (0, 40, 65), (0, 40, 10), (0, 40, 100)]:
         want = whole.search(q[lo:hi], wa[lo:hi], wb[lo:hi], k=kk)
+        gotd = sh.search(qd[lo:hi], wa[lo:hi], wb[lo:hi], k=kk, to_host=False)
         got = sh.search(q[lo:hi], wa[lo:hi], wb[lo:hi], k=kk, to_host=True)
+        if not np.array_equal(gotd.indices.cpu().numpy(), got.indices):
+            print(f"rank {rank} case {(lo, hi, kk)}: device variant != host variant", flush=True)
         nccl_like = part.search_candidates(q[lo:hi], wa[lo:hi], wb[lo:hi], k=kk)
         torch.cuda.synchronize()
         bad_w = bad_g = 0
@@ -43,4 +49,4 @@ def worker(rank, world, port):
 
 if __name__ == "__main__":
     import torch.multiprocessing as mp
-    mp.spawn(worker, args=(2, 29711), nprocs=2)
+    mp.spawn(worker, args=(2, 29711, "--two-gpus" in sys.argv), nprocs=2)
