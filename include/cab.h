@@ -154,10 +154,12 @@ CAB_API int cab_index_file_info(const char *path, int *dim, int *dtype, int64_t 
  * A query holding NaN/Inf (sklearn raises ValueError for the reference): with host outputs the
  * call fails with CAB_ERR_NONFINITE; with device outputs (nothing is read back, the call does
  * not wait) that query gets out_count = -1 and no results, the other queries are unaffected.
- * Stream contract: consecutive calls on one handle go to the same stream (or the caller orders
- * the streams); a search is launched so that it may START before the previous search on that
- * stream has finished (programmatic dependent launch) but never reads a device query before the
- * kernel in front of it has completed -- unless option "queries_settled" is set. */
+ * Stream contract: calls on one handle share its workspace and are ordered by the stream they
+ * run on; a call that arrives on a different stream than the previous one first waits for the
+ * device (so a device-tensor call on the caller's stream may be followed by a host call on the
+ * handle's own stream).  On one stream a search is launched so that it may START before the
+ * previous search has finished (programmatic dependent launch) but never reads a device query
+ * before the kernel in front of it has completed -- unless option "queries_settled" is set. */
 CAB_API int cab_search(cab_index *idx, const float *queries, int queries_loc, const double *w_asr,
                const double *w_audio, int n_queries, int k, double threshold, int path,
                int64_t *out_index, double *out_fusion, float *out_asr, float *out_audio,
@@ -218,6 +220,11 @@ CAB_API int cab_search_sharded(cab_index *idx, const float *queries, int queries
                                const double *w_audio, int n_queries, int k, double threshold, int path,
                                int64_t *out_index, double *out_fusion, float *out_asr, float *out_audio,
                                uint8_t *out_flags, int32_t *out_count, int out_loc, void *stream);
+
+/* Diagnostic: copy this rank's whole exchange buffer to the host after a device synchronise --
+ * [256 bytes: epoch flags 2 x world u32][2 halves x world x max_queries x max_k cab_candidate].
+ * `needed` (may be NULL) receives its size; out == NULL only queries the size. */
+CAB_API int cab_peer_snapshot(cab_index *idx, void *out, size_t out_bytes, size_t *needed);
 
 /* Diagnostic (option "stamp_exchange" = 1): %globaltimer stamps, in ns, of the last sharded
  * searches whose merge ran inside the finalize kernel -- per search {scan complete, own epoch flag

@@ -66,6 +66,7 @@ SIGNATURES = {
     "cab_peer_attach": (_i32, [_p, _p]),
     "cab_search_sharded": (_i32, [_p, _p, _i32, _p, _p, _i32, _i32, _dbl, _i32, _p, _p, _p, _p, _p, _p, _i32, _p]),
     "cab_index_exchange_stamps": (_i32, [_p, _p, _i32]),
+    "cab_peer_snapshot": (_i32, [_p, _p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "cab_index_set_option": (_i32, [_p, C.c_char_p, _i64]),
     "cab_index_get_option": (_i64, [_p, C.c_char_p]),
     "cab_index_launch_count": (_i64, [_p]),

@@ -76,6 +76,11 @@ struct cab_index {
     uint32_t peer_epoch = 0;
     unsigned int *d_done = nullptr;
     int *d_status = nullptr;
+    // Stream of the previous search / scoring call.  The workspace (partial lists, ticket counters,
+    // parameter block, exchange buffers) is shared by consecutive calls, which are ordered by the
+    // stream they run on; a call that arrives on ANOTHER stream first waits for the device.
+    cudaStream_t last_stream = nullptr;
+    bool last_stream_set = false;
     unsigned long long *d_stamps = nullptr;          // [kStampRows][4] %globaltimer stamps of the last sharded searches
     uint32_t stamp_calls = 0;
     unsigned int *d_host_done = nullptr;             // CTA counter for host-visible completion
@@ -109,6 +114,18 @@ static int fail(cab_index *idx, int code, const char *fmt, ...) {
         if (!(idx)) return fail(nullptr, CAB_ERR_INVALID, "null index handle");  \
         if ((idx)->sticky != CAB_OK) return (idx)->sticky;                       \
     } while (0)
+
+// Calls on one handle share its workspace and are ordered by their stream.  A caller that moves to
+// another stream (e.g. a device-tensor call on torch's stream followed by a host call on the
+// handle's own stream) gets the ordering it implicitly expects: the device is drained once.
+static int enter_stream(cab_index *idx, cudaStream_t s) {
+    if (idx->last_stream_set && idx->last_stream != s) {
+        CU(idx, cudaSetDevice(idx->device));
+        CU(idx, cudaDeviceSynchronize());
+    }
+    idx->last_stream = s; idx->last_stream_set = true;
+    return CAB_OK;
+}
 
 static size_t elem_size(int dtype) { return dtype == CAB_BF16 ? 2 : 4; }
 static size_t align_up(size_t x, size_t a);
@@ -908,7 +925,9 @@ int cab_search(cab_index *idx, const float *queries, int queries_loc, const doub
     CHECK_HANDLE(idx);
     cudaStream_t s = stream ? (cudaStream_t)stream : idx->own_stream;
     const UserOut o{out_index, out_fusion, out_asr, out_audio, out_flags, out_count, out_loc};
-    int rc = run_local(idx, queries, queries_loc, w_asr, w_audio, n_queries, k, threshold, path, &o, nullptr, nullptr, s);
+    int rc = enter_stream(idx, s);
+    if (rc != CAB_OK) return rc;
+    rc = run_local(idx, queries, queries_loc, w_asr, w_audio, n_queries, k, threshold, path, &o, nullptr, nullptr, s);
     if (rc != CAB_OK) return rc;
     return finish_outputs(idx, n_queries, k, o, s);
 }
@@ -919,7 +938,9 @@ int cab_search_candidates(cab_index *idx, const float *queries, int queries_loc,
     CHECK_HANDLE(idx);
     if (!out_device) return fail(idx, CAB_ERR_INVALID, "out_device is null");
     cudaStream_t s = stream ? (cudaStream_t)stream : idx->own_stream;
-    int rc = run_local(idx, queries, queries_loc, w_asr, w_audio, n_queries, k, threshold, path, nullptr, out_device, nullptr, s);
+    int rc = enter_stream(idx, s);
+    if (rc != CAB_OK) return rc;
+    rc = run_local(idx, queries, queries_loc, w_asr, w_audio, n_queries, k, threshold, path, nullptr, out_device, nullptr, s);
     if (rc != CAB_OK) return rc;
     if (idx->opt_sync) CU(idx, cudaStreamSynchronize(s));
     return CAB_OK;
@@ -940,8 +961,9 @@ int cab_merge_candidates(cab_index *idx, const cab_candidate *cands_device, int 
     if (out_loc != CAB_HOST && out_loc != CAB_DEVICE) return fail(idx, CAB_ERR_INVALID, "out_loc");
     CU(idx, cudaSetDevice(idx->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : idx->own_stream;
-    int rc = ensure_workspace(idx, n_queries, k, 1, 1, k, 0);
+    int rc = enter_stream(idx, s);
     if (rc != CAB_OK) return rc;
+    if ((rc = ensure_workspace(idx, n_queries, k, 1, 1, k, 0))) return rc;
     if (w_asr && (rc = stage_params(idx, nullptr, CAB_DEVICE, w_asr, w_audio, n_queries, s, nullptr))) return rc;
     const UserOut o{out_index, out_fusion, out_asr, out_audio, out_flags, out_count, out_loc};
     EmitArgs ea{};
@@ -968,6 +990,10 @@ int cab_score_all(cab_index *idx, const float *queries, int queries_loc, int n_q
     if (idx->size == 0) return CAB_OK;
     cudaStream_t s = stream ? (cudaStream_t)stream : idx->own_stream;
     CU(idx, cudaSetDevice(idx->device));
+    {
+        int rc = enter_stream(idx, s);
+        if (rc != CAB_OK) return rc;
+    }
     const bool host_out = out_loc == CAB_HOST;
     const size_t per_query = size_t(idx->size) * sizeof(float);
     float *d_out = out;
@@ -1092,7 +1118,9 @@ int cab_search_sharded(cab_index *idx, const float *queries, int queries_loc, co
         pp.bufs[r] = reinterpret_cast<cab_candidate *>(idx->peer_ptr[r] + peer_flags_bytes()) + size_t(pp.parity) * half;
     }
     const UserOut o{out_index, out_fusion, out_asr, out_audio, out_flags, out_count, out_loc};
-    int rc = run_local(idx, queries, queries_loc, w_asr, w_audio, n_queries, k, threshold, path, &o, nullptr, &sh, s);
+    int rc = enter_stream(idx, s);
+    if (rc != CAB_OK) return rc;
+    rc = run_local(idx, queries, queries_loc, w_asr, w_audio, n_queries, k, threshold, path, &o, nullptr, &sh, s);
     if (rc != CAB_OK) return rc;
     if (!sh.fused) {
         // many queries / several scan passes / an empty shard: the merge is its own launch
@@ -1109,6 +1137,19 @@ int cab_search_sharded(cab_index *idx, const float *queries, int queries_loc, co
         CU(idx, cudaGetLastError());
     }
     return finish_outputs(idx, n_queries, k, o, s);
+}
+
+int cab_peer_snapshot(cab_index *idx, void *out, size_t out_bytes, size_t *needed) {
+    CHECK_HANDLE(idx);
+    if (!idx->d_peer) return fail(idx, CAB_ERR_INVALID, "cab_peer_init first");
+    const size_t bytes = peer_flags_bytes() + 2 * peer_half_elems(idx) * sizeof(cab_candidate);
+    if (needed) *needed = bytes;
+    if (!out) return CAB_OK;
+    if (out_bytes < bytes) return fail(idx, CAB_ERR_INVALID, "snapshot buffer too small (%zu < %zu)", out_bytes, bytes);
+    CU(idx, cudaSetDevice(idx->device));
+    CU(idx, cudaDeviceSynchronize());
+    CU(idx, cudaMemcpy(out, idx->d_peer, bytes, cudaMemcpyDeviceToHost));
+    return CAB_OK;
 }
 
 int cab_index_exchange_stamps(cab_index *idx, uint64_t *out, int max_rows) {

@@ -82,11 +82,10 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
     return v;
 }
 // A candidate record read from L2 (ld.global.cg), never from L1: exchange buffers are written by
-// peers over NVLink (and by this GPU's earlier kernels) while the reading kernel may already be
-// resident -- it is launched early, by programmatic dependent launch, while its predecessor still
-// runs -- so a line cached in this SM's L1 by the merge of two searches ago would be served stale
-// (seen on two B200s: the merge mixed in the candidates of an earlier call).  24-byte records are
-// 8-byte aligned: three 64-bit loads.
+// peers over NVLink while the reading kernel is already resident (it is launched early, by
+// programmatic dependent launch, and then spins on the peers' flags), so nothing orders an L1
+// invalidation between a line cached by the merge of two searches ago and this read.  24-byte
+// records are 8-byte aligned: three 64-bit loads.
 __device__ __forceinline__ cab_candidate load_candidate_l2(const cab_candidate *p) {
     const long long *p64 = reinterpret_cast<const long long *>(p);
     const long long w0 = __ldcg(p64), w1 = __ldcg(p64 + 1), w2 = __ldcg(p64 + 2);

@@ -127,6 +127,14 @@ class SegmentIndex:
     def last_scan_ms(self) -> float:
         return float(self._lib.cab_index_last_scan_ms(self._h))
 
+    def peer_snapshot(self) -> np.ndarray:
+        """Diagnostic: this rank's exchange buffer as raw bytes (layout in include/cab.h)."""
+        need = C.c_size_t()
+        N.check(self._lib.cab_peer_snapshot(self._h, None, 0, C.byref(need)), self._h)
+        out = np.zeros(need.value, dtype=np.uint8)
+        N.check(self._lib.cab_peer_snapshot(self._h, _ptr(out), out.size, None), self._h)
+        return out
+
     def exchange_stamps(self, max_rows: int = 64) -> np.ndarray:
         """Option "stamp_exchange": uint64 [n, 4] %globaltimer ns of the last sharded searches --
         {scan complete, own flag raised, all ranks' flags seen, results written} (oldest first)."""

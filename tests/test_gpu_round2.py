@@ -317,3 +317,26 @@ def test_raw_dot_product_scoring_for_non_unit_embeddings(dtype, rel, tmp_path):
     r2 = again.search(q, 0.4, 0.6, k=20)
     assert r2.indices.tolist() == res.indices.tolist() and r2.fusion.tolist() == res.fusion.tolist()
     idx.close(); again.close()
+
+
+def test_alternating_device_and_host_calls_on_one_handle():
+    """A device-tensor search runs on torch's stream and returns without waiting; a host search on
+    the same handle runs on the handle's own stream.  Both use the handle's workspace (partial
+    lists, chunk tickets): the second call must be ordered after the first (found on two B200s: the
+    two multi-batch scans ran concurrently and each lost rows)."""
+    torch = pytest.importorskip("torch")
+    seed, n, nq = 31, 400_000, 80
+    idx = _lib(seed, n, nq, 30, "fp32", partial=True)
+    q = synth.raw_queries(seed, 0, nq)
+    qd = torch.from_numpy(q).cuda()
+    wa = np.linspace(0.2, 0.8, nq); wb = 1 - wa
+    want_a = idx.search(q[:40], wa[:40], wb[:40], k=100)
+    want_b = idx.search(q[40:], wa[40:], wb[40:], k=100)
+    for _ in range(6):
+        dev = idx.search(qd[:40], wa[:40], wb[:40], k=100)            # async, torch's stream
+        host = idx.search(q[40:], wa[40:], wb[40:], k=100)            # handle's own stream, right behind it
+        dev2 = idx.search(qd[:40], wa[:40], wb[:40], k=100)
+        np.testing.assert_array_equal(host.indices, want_b.indices)
+        np.testing.assert_array_equal(dev.indices.cpu().numpy(), want_a.indices)
+        np.testing.assert_array_equal(dev2.indices.cpu().numpy(), want_a.indices)
+    idx.close()

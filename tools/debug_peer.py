@@ -39,6 +39,24 @@ def worker(rank, world, port, two_gpus):
             o = no.search(q[lo + j], a, b, f, wa[lo + j], wb[lo + j], k=kk)
             bad_w += list(want.indices[j, :len(o.indices)]) != list(o.indices)
             bad_g += list(got.indices[j, :len(o.indices)]) != list(o.indices)
+        if os.environ.get("SNAP") and bad_g:
+            # what does the exchange buffer hold?  expected: every rank's search_candidates block
+            mine = nccl_like.cpu().numpy().copy()                      # [Q, k, 24] u8
+            blocks = [None] * world
+            dist.all_gather_object(blocks, mine)
+            snap = part.peer_snapshot()
+            flags = snap[:16].view(np.uint32)
+            half = world * 64 * 100
+            body = snap[256:].reshape(2, half, 24)
+            nqc = hi - lo
+            for par in (0, 1):
+                for r in range(world):
+                    seg = body[par, r * nqc * kk:(r + 1) * nqc * kk].reshape(nqc, kk, 24)
+                    same = (seg == blocks[r]).all(axis=(1, 2))
+                    idxs = seg.view(np.int64)[..., 0] if False else np.ascontiguousarray(seg[..., :8]).view(np.int64)[..., 0]
+                    print(f"  rank {rank} snapshot parity {par} list {r}: queries equal to rank {r}'s candidates: {int(same.sum())}/{nqc}; "
+                          f"first mismatching query {int(np.argmin(same)) if not same.all() else -1}; flags {flags.tolist()}; "
+                          f"q0 first idx {idxs[0, :3].tolist()} expected {np.ascontiguousarray(blocks[r][0, :3, :8]).view(np.int64)[:, 0].tolist()}", flush=True)
         cand = nccl_like.cpu().numpy().view(np.dtype([("index", "<i8"), ("a", "<f4"), ("b", "<f4"), ("fl", "<u4"), ("pad", "<u4")]))
         print(f"rank {rank} case {(lo, hi, kk)}: whole!=oracle {bad_w}, sharded!=oracle {bad_g}; "
               f"q0 sharded rows>=per: {(got.indices[0] >= per).sum()} want: {(want.indices[0] >= per).sum()}; "
