@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 NG=$(nvidia-smi -L | wc -l)
 echo "visible GPUs: $NG"
 echo "== two-device / peer tests"; timeout 600 python -m pytest tests/test_gpu_round2.py -m gpu -q > gpurun_out/pytest_multi.log 2>&1; echo "rc=$?"; tail -5 gpurun_out/pytest_multi.log
-for N in 1 2 4 8; do
+for N in ${NS:-1 2 4 8}; do
   [ $N -le $NG ] || continue
   echo "== bench N=$N"
   if [ $N -eq 1 ]; then
