@@ -107,18 +107,22 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 
 // Store `n` candidates (shared memory) of query q into every rank's exchange buffer and, once
 // every CTA of the (last) launch has done so, raise this rank's epoch flag on every rank.
-// Thread t stores candidate t % k on rank t / k: all world x k records leave in parallel.  Only the
-// storing threads pay the system-scope fence; the release store of the flag orders the rest.
+// Thread t stores candidate t % k on rank t / k: all world x k records leave in parallel.  The
+// stores are ordered before the flag by the CTA barrier + ONE system-scope fence + release store in
+// the signalling threads (fences are cumulative over everything that happens before them), so the
+// NVLink round trip is paid once, not once per storing thread and again for the flag.
 // Called by all threads of the CTA.
 __device__ __forceinline__ void peer_push_and_signal(const PeerPush &p, const cab_candidate *cand, int q, int k,
                                                      int *s_last) {
     for (int t = threadIdx.x; t < p.world * k; t += blockDim.x) {
         const int r = t / k, i = t - r * k;
         p.bufs[r][peer_slot(p, q, k, i)] = cand[i];
-        __threadfence_system();                   // this thread's peer store is performed system-wide
     }
     __syncthreads();
-    if (!p.signal) return;
+    if (!p.signal) {                              // an earlier batch of the call: its stores must be performed
+        if (threadIdx.x == 0) __threadfence_system();   // system-wide before this grid completes
+        return;
+    }
     if (gridDim.x > 1) {                          // several queries: the last CTA to finish raises the flags
         if (threadIdx.x == 0) {
             __threadfence();
@@ -140,16 +144,17 @@ __device__ __forceinline__ void peer_push_and_signal(const PeerPush &p, const ca
 // all threads of every CTA after their output stores.
 __device__ __forceinline__ void host_signal(const EmitArgs &e) {
     if (!e.done_flag) return;
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0 && e.done_epoch) {
+    __syncthreads();                              // the CTA's output stores happen before thread 0's fence
+    if (threadIdx.x != 0) return;
+    __threadfence_system();                       // cumulative: performs them at system scope (PCIe)
+    if (!e.done_epoch) return;                    // an earlier batch of the call does not signal
+    if (gridDim.x > 1) {
         const unsigned prev = atomicAdd(e.done_counter, 1u);
-        if (prev == gridDim.x - 1) {
-            *e.done_counter = 0u;
-            __threadfence_system();
-            st_release_sys(e.done_flag, e.done_epoch);
-        }
+        if (prev != gridDim.x - 1) return;
+        *e.done_counter = 0u;
+        __threadfence_system();                   // acquire side of the other CTAs' counts
     }
+    st_release_sys(e.done_flag, e.done_epoch);
 }
 
 // Wait until the epoch flags of all `n_lists` ranks hold `epoch` (their candidates of this search

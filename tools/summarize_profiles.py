@@ -17,8 +17,9 @@ workload = sys.argv[2] if len(sys.argv) > 2 else "1m_fp32_q1_top10"
 os.makedirs(PROF, exist_ok=True)
 
 # ---- launch list -----------------------------------------------------------------------------
-lp = os.path.join(OUT, "launches.csv")
-if os.path.exists(lp):
+for lp, workload_ in ((os.path.join(OUT, "launches.csv"), workload), (os.path.join(OUT, "launches_gemm.csv"), "10m_bf16_q256_top100")):
+    if not os.path.exists(lp):
+        continue
     rows = list(csv.reader(open(lp)))
     h = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
     H = rows[h]
@@ -29,13 +30,13 @@ if os.path.exists(lp):
         if len(r) > vi:
             d[r[ki]].append(float(r[vi].replace(",", "")) / 1e3)
             order.append((r[ki], float(r[vi].replace(",", "")) / 1e3))
-    with open(os.path.join(PROF, f"{tag}_launches_{workload}.md"), "w") as f:
-        f.write(f"# ncu launch list -- bench.py --steps 5 --warmup 3 ({workload}), {tag}\n\n"
+    with open(os.path.join(PROF, f"{tag}_launches_{workload_}.md"), "w") as f:
+        f.write(f"# ncu launch list -- bench.py --steps 5 (3 for the tensor-core workload) --warmup 3 --reps 1 ({workload_}), {tag}\n\n"
                 "`ncu --metrics gpu__time_duration.sum --clock-control none` (cold-cache, serialised: "
                 "compare shares, not absolutes).\n\n| kernel | launches | mean us | min us | max us |\n|---|---:|---:|---:|---:|\n")
         for k, v in d.items():
             f.write(f"| `{k[:70]}` | {len(v)} | {sum(v)/len(v):.1f} | {min(v):.1f} | {max(v):.1f} |\n")
-        step = [(k, t) for k, t in order if "gemv_scan" in k or "finalize" in k or "emit" in k or "gemm" in k]
+        step = [(k, t) for k, t in order if "cab_scan" in k or "gemv_scan" in k or "finalize" in k or "emit" in k or "gemm" in k]
         if step:
             tot = sum(t for _, t in step)
             f.write("\nShare of the search step (scan + finalize [+ emit]) by kernel:\n\n")
@@ -59,6 +60,7 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__cycles_elapsed.avg", "smsp__cycles_active.avg"]
 traffic = {}
 REPORT_WORKLOAD = {"prof_gemv": "1m_fp32_q1_top10", "prof_gemm": "10m_bf16_q256_top100",
+                   "prof_gemv10m": "10m_fp32_q1_top10", "prof_finalize": "finalize_1m_fp32_q1_top10",
                    "prof_score_all": "score_all_10m_fp32"}
 for rep in sorted(f for f in os.listdir(OUT) if f.endswith(".ncu-rep")):
     r = subprocess.run(["ncu", "-i", os.path.join(OUT, rep), "--page", "raw", "--csv"], capture_output=True, text=True)
