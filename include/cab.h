@@ -227,8 +227,9 @@ CAB_API int cab_search_sharded(cab_index *idx, const float *queries, int queries
 CAB_API int cab_peer_snapshot(cab_index *idx, void *out, size_t out_bytes, size_t *needed);
 
 /* Diagnostic (option "stamp_exchange" = 1): %globaltimer stamps, in ns, of the last sharded
- * searches whose merge ran inside the finalize kernel -- per search {scan complete, own epoch flag
- * raised on every rank, all ranks' flags seen, results written}.  Copies up to max_rows rows of 4
+ * searches whose merge ran inside the finalize kernel -- per search a row of 8 uint64:
+ * {scan complete, best k selected (dependents released), winners re-scored, own epoch flag raised
+ * on every rank, all ranks' flags seen, results written, 0, 0}.  Copies up to max_rows rows
  * (oldest first) into `out` (host) and returns the number of rows copied (0 on error, with
  * cab_last_error set).  Synchronises the device.  NOTE: returns a row count, not a cab_status. */
 CAB_API int cab_index_exchange_stamps(cab_index *idx, uint64_t *out, int max_rows);

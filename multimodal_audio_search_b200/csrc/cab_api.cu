@@ -129,7 +129,7 @@ static int enter_stream(cab_index *idx, cudaStream_t s) {
 
 static size_t elem_size(int dtype) { return dtype == CAB_BF16 ? 2 : 4; }
 static size_t align_up(size_t x, size_t a);
-constexpr int kStampRows = 64;
+constexpr int kStampRows = 64, kStampCols = 8;
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int cab_version(void) { return CAB_VERSION; }
@@ -808,7 +808,7 @@ static int run_local(cab_index *idx, const float *queries, int queries_loc, cons
         ea.wait_flags = peer->flags[peer->rank] + peer->parity * peer->world;
         ea.wait_epoch = peer->epoch;
         ea.status = idx->d_status;
-        if (idx->opt_stamp_exchange && idx->d_stamps) ea.stamps = idx->d_stamps + size_t(idx->stamp_calls++ % kStampRows) * 4;
+        if (idx->opt_stamp_exchange && idx->d_stamps) ea.stamps = idx->d_stamps + size_t(idx->stamp_calls++ % kStampRows) * kStampCols;
     }
     idx->timed = false;
     cab_candidate *cands = cand_dst ? cand_dst : idx->d_cands;      // cab_search_candidates: straight into the caller's block
@@ -1070,8 +1070,8 @@ int cab_peer_init(cab_index *idx, int rank, int world, int max_queries, int max_
     CU(idx, cudaMemset(idx->d_done, 0, sizeof(unsigned int)));
     CU(idx, cudaMalloc((void **)&idx->d_status, sizeof(int)));
     CU(idx, cudaMemset(idx->d_status, 0, sizeof(int)));
-    CU(idx, cudaMalloc((void **)&idx->d_stamps, size_t(kStampRows) * 4 * sizeof(unsigned long long)));
-    CU(idx, cudaMemset(idx->d_stamps, 0, size_t(kStampRows) * 4 * sizeof(unsigned long long)));
+    CU(idx, cudaMalloc((void **)&idx->d_stamps, size_t(kStampRows) * kStampCols * sizeof(unsigned long long)));
+    CU(idx, cudaMemset(idx->d_stamps, 0, size_t(kStampRows) * kStampCols * sizeof(unsigned long long)));
     CU(idx, cudaDeviceSynchronize());
     cudaIpcMemHandle_t h;
     CU(idx, cudaIpcGetMemHandle(&h, idx->d_peer));
@@ -1159,12 +1159,12 @@ int cab_index_exchange_stamps(cab_index *idx, uint64_t *out, int max_rows) {
     CU(idx, cudaSetDevice(idx->device));
     const int have = int(std::min<uint32_t>(idx->stamp_calls, kStampRows));
     const int n = std::min(have, max_rows);
-    std::vector<unsigned long long> all(size_t(kStampRows) * 4);
+    std::vector<unsigned long long> all(size_t(kStampRows) * kStampCols);
     CU(idx, cudaDeviceSynchronize());
     CU(idx, cudaMemcpy(all.data(), idx->d_stamps, all.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     for (int i = 0; i < n; ++i) {                    // oldest first among the last n
         const uint32_t call = idx->stamp_calls - uint32_t(n) + uint32_t(i);
-        memcpy(out + size_t(i) * 4, all.data() + size_t(call % kStampRows) * 4, 4 * sizeof(uint64_t));
+        memcpy(out + size_t(i) * kStampCols, all.data() + size_t(call % kStampRows) * kStampCols, kStampCols * sizeof(uint64_t));
     }
     return n;
 }

@@ -479,6 +479,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, E
         trim();
     }
     int n_win = s_cnt;
+    if (stamp) e.stamps[1] = globaltimer_ns();
 
     // Everything the next scan on this stream touches -- its ticket counters (reset above), the
     // partial-key slots, counts and levels (all consumed into shared memory by now) -- is released:
@@ -523,16 +524,17 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, E
         }
     }
     __syncthreads();
+    if (stamp) e.stamps[2] = globaltimer_ns();
     uint64_t *score = s_sort;                                        // the selection buffer is free now
     int64_t *index = reinterpret_cast<int64_t *>(s_sort + kEmitMax);
     uint16_t *pos = reinterpret_cast<uint16_t *>(s_sort + 2 * kEmitMax);
     if (a.peer.world) {
         // sharded search: this shard's candidates go to every rank over NVLink peer memory
         peer_push_and_signal(a.peer, s_cand, a.peer.q0 + qi, a.k, &s_last);
-        if (stamp) e.stamps[1] = globaltimer_ns();
+        if (stamp) e.stamps[3] = globaltimer_ns();
         if (!e.out_index) return;                                    // merged by a separate emit launch
         wait_peer_flags(e.wait_flags, e.n_lists, e.wait_epoch, e.status);
-        if (stamp) e.stamps[2] = globaltimer_ns();
+        if (stamp) e.stamps[4] = globaltimer_ns();
         const cab_candidate *lists = e.cands;                        // [n_lists][n_queries][k], this rank's buffer
         const int nq = e.n_queries, k = e.k;
         emit_ranked([&](int t) {
@@ -540,7 +542,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, E
             return load_candidate_l2(lists + (size_t(list) * nq + qi) * k + i);
         }, e.n_lists * k, qi, e, !finite, score, index, pos);
         host_signal(e);
-        if (stamp) e.stamps[3] = globaltimer_ns();
+        if (stamp) e.stamps[5] = globaltimer_ns();
         return;
     }
     if (!e.out_index) return;          // candidates only (cab_search_candidates)

@@ -204,8 +204,9 @@ struct EmitArgs {
     const uint32_t *wait_flags;   // null = no wait
     uint32_t wait_epoch;
     int *status;                  // set to 7 (and the kernel traps) if the wait times out
-    // sharded search, diagnostic: %globaltimer (ns) at {scan complete, own flag raised, all flags
-    // seen, results written} of query 0's CTA; null = not recorded
+    // sharded search, diagnostic: %globaltimer (ns) at {scan complete, best k selected (dependents
+    // released), winners re-scored, own flag raised, all flags seen, results written} of query 0's
+    // CTA, 8 slots per search (2 unused); null = not recorded
     unsigned long long *stamps;
 };
 // cab_candidate.index of every slot of a query that holds NaN/Inf (travels through the exchange so

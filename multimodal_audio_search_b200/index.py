@@ -136,11 +136,12 @@ class SegmentIndex:
         return out
 
     def exchange_stamps(self, max_rows: int = 64) -> np.ndarray:
-        """Option "stamp_exchange": uint64 [n, 4] %globaltimer ns of the last sharded searches --
-        {scan complete, own flag raised, all ranks' flags seen, results written} (oldest first)."""
-        out = np.zeros((max_rows, 4), dtype=np.uint64)
+        """Option "stamp_exchange": uint64 [n, 6] %globaltimer ns of the last sharded searches --
+        {scan complete, best k selected, winners re-scored, own flag raised, all ranks' flags seen,
+        results written} (oldest first)."""
+        out = np.zeros((max_rows, 8), dtype=np.uint64)
         n = int(self._lib.cab_index_exchange_stamps(self._h, _ptr(out), int(max_rows)))
-        return out[:n]
+        return out[:n, :6]
 
     def _stream(self):
         """torch's current stream for the C-ABI.  NULL means "the handle's own stream" there, and
