@@ -134,10 +134,9 @@ __device__ __forceinline__ void peer_push_and_signal(const PeerPush &p, const ca
         __syncthreads();
         if (!*s_last) return;
     }
-    if (threadIdx.x < p.world) {
-        __threadfence_system();
-        st_release_sys(p.flags[threadIdx.x] + p.parity * p.world + p.rank, p.epoch);
-    }
+    // st.release.sys = system-scope fence (cumulative over the CTA's stores, which the barrier above
+    // ordered before it) + store: one NVLink round trip
+    if (threadIdx.x < p.world) st_release_sys(p.flags[threadIdx.x] + p.parity * p.world + p.rank, p.epoch);
 }
 
 // Host-visible completion of a launch whose outputs live in mapped pinned host memory: called by
@@ -348,10 +347,15 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, E
         }
         __syncthreads();
         const uint64_t bound = s_bound;                              // 0 if fewer than k non-empty lists
-        for (int base = 0; base < total; base += kFinThreads) {
-            const int i = base + threadIdx.x;
-            const uint64_t key = i < total ? slots[i] : 0ull;
-            append(key > bound, key);
+        for (int base = 0; base < total; base += kFinThreads * 4) {  // 4 independent loads in flight per thread
+            uint64_t key[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = base + u * kFinThreads + threadIdx.x;
+                key[u] = i < total ? slots[i] : 0ull;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) append(key[u] > bound, key[u]);
         }
         __syncthreads();
         const int S = s_cnt;
@@ -500,24 +504,27 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, E
         const int i = i0 + sub;
         const bool have = i < n_win;                       // uniform within a lane group
         const uint32_t row = have ? key_row(s_sort[i]) : 0u;
-        float sa = 0.f, sb = 0.f;
+        float sa = 0.f, sb = 0.f, len_a = 1.f, len_b = 1.f;
+        uint32_t row_flags = 0u;
         if (have) {
             const uint4 *pa = A + size_t(row) * TR::CPR + g;
             const uint4 *pb = B + size_t(row) * TR::CPR + g;
             uint4 ca[3], cb[3];
 #pragma unroll
             for (int j = 0; j < 3; ++j) { ca[j] = pa[TR::G * j]; cb[j] = pb[TR::G * j]; }
+            row_flags = a.flags[row];                      // in flight together with the row (one round trip, not two)
+            if (a.norm_asr) { len_a = a.norm_asr[row]; len_b = a.norm_audio[row]; }
 #pragma unroll
             for (int j = 0; j < 3; ++j) { sa = dot_chunk<DT>(ca[j], q, j, sa); sb = dot_chunk<DT>(cb[j], q, j, sb); }
         }
         sa = group_sum<DT>(sa);
         sb = group_sum<DT>(sb);
-        if (a.norm_asr && have) { sa *= a.norm_asr[row]; sb *= a.norm_audio[row]; }      // raw dot products
+        sa *= len_a; sb *= len_b;                          // raw dot products (option raw_dot), else x 1
         if (g == 0 && i < a.k) {
             cab_candidate c;
             c.index = have ? a.row_base + int64_t(row) : (finite ? int64_t(-1) : kBadQueryIndex);
             c.asr_sim = sa; c.audio_sim = sb;
-            c.flags = have ? uint32_t(a.flags[row]) : 0u;
+            c.flags = row_flags;
             c.pad = 0u;
             if (out) out[i] = c;
             s_cand[i] = c;

@@ -229,6 +229,8 @@ class SegmentIndex:
     @staticmethod
     def _weights(w_asr, w_audio, nq):
         """Owned float64 [nq] arrays (scalars broadcast)."""
+        if nq == 1 and isinstance(w_asr, float) and isinstance(w_audio, float):      # the drop-in's call: two Python floats
+            return np.array([w_asr]), np.array([w_audio])
         wa = np.asarray(w_asr, dtype=np.float64).reshape(-1)
         wb = np.asarray(w_audio, dtype=np.float64).reshape(-1)
         if wa.size != nq:
