@@ -81,11 +81,12 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// A candidate record read from L2 (ld.global.cg), never from L1: exchange buffers are written by
-// peers over NVLink while the reading kernel is already resident (it is launched early, by
-// programmatic dependent launch, and then spins on the peers' flags), so nothing orders an L1
-// invalidation between a line cached by the merge of two searches ago and this read.  24-byte
-// records are 8-byte aligned: three 64-bit loads.
+// A candidate record read from L2 (ld.global.cg), never from L1.  Exchange buffers are written by
+// peers over NVLink while the reading kernel is already resident (launched early by programmatic
+// dependent launch, then spinning on the peers' flags).  The acquire load of a flag is followed
+// by an L1 invalidation (CCTL.IVALL in the SASS), which by itself covers the plain loads after the
+// barrier; bypassing L1 for the records makes the merge independent of that detail and keeps
+// 24 KB of use-once data out of L1.  24-byte records are 8-byte aligned: three 64-bit loads.
 __device__ __forceinline__ cab_candidate load_candidate_l2(const cab_candidate *p) {
     const long long *p64 = reinterpret_cast<const long long *>(p);
     const long long w0 = __ldcg(p64), w1 = __ldcg(p64 + 1), w2 = __ldcg(p64 + 2);
