@@ -623,7 +623,9 @@ def main():
         # sharded search sees a superset of the single index's candidates there.
         tol = 1e-5
         exact, within, n, detail = 0, 0, 0, []
-        cases = [(i, i + 1, 10) for i in range(8)] + [(8, 9, 100), (0, 40, 10), (9, 10, 10), (0, 40, 100)]
+        # single queries (merge fused into the finalize kernel, one CTA), small batches (fused, several CTAs
+        # behind one per-rank flag), two scan passes (separate merge launch), k = 10 / 100
+        cases = [(i, i + 1, 10) for i in range(8)] + [(8, 9, 100), (2, 9, 10), (0, 32, 100), (0, 40, 10), (9, 10, 10), (0, 40, 100)]
         for lo, hi, kk in cases:
             want = whole.search(q[lo:hi], wa[lo:hi], wb[lo:hi], k=kk)
             got = sh.search(qd[lo:hi], wa[lo:hi], wb[lo:hi], k=kk, to_host=False)

@@ -232,6 +232,17 @@ def _peer_worker(rank, world, port, seed, n, nq, out_path):
             fus = r.fusion if to_host else r.fusion.cpu().numpy()
             cnt = r.count if to_host else r.count.cpu().numpy()
             res[f"i{rep}_{ci}"], res[f"f{rep}_{ci}"], res[f"c{rep}_{ci}"] = ind, fus, cnt
+    # a library so small that the second rank's shard is EMPTY (nothing to scan: it pushes empty lists)
+    tiny = SegmentIndex("fp32", capacity=8, device=0)
+    t_lo, t_hi = (0, 3) if rank == 0 else (3, 3)                   # all 3 rows on rank 0
+    if t_hi > t_lo:
+        tiny.append_synth(seed + 7, 3, t_lo, t_hi, n_queries=1, plants=3)
+    tiny.row_base = t_lo
+    sh2 = ShardedSearcher(tiny, rank, world, exchange="p2p", max_queries=4, max_k=16)
+    q2 = synth.raw_queries(seed + 7, 0, 1)
+    for rep in range(2):
+        r = sh2.search(q2, 0.5, 0.5, k=10, threshold=-1.0, to_host=True)
+        res[f"tiny_i{rep}"], res[f"tiny_f{rep}"], res[f"tiny_c{rep}"] = r.indices, r.fusion, r.count
     torch.cuda.synchronize()
     dist.barrier()
     np.savez(out_path + f".{rank}.npz", **res)
@@ -265,9 +276,16 @@ def test_peer_exchange_two_processes_one_gpu(tmp_path):
             for p in ctx.processes:
                 p.kill()
             pytest.fail("peer exchange workers did not finish")
+    tiny = SegmentIndex("fp32", capacity=8)
+    tiny.append_synth(seed + 7, 3, 0, 3, n_queries=1, plants=3)
+    tiny_want = tiny.search(synth.raw_queries(seed + 7, 0, 1), 0.5, 0.5, k=10, threshold=-1.0)
+    tiny.close()
+    assert tiny_want.count[0] >= 1
     for rank in range(world):
         z = np.load(out + f".{rank}.npz")
         for rep in range(2):
+            np.testing.assert_array_equal(z[f"tiny_i{rep}"], tiny_want.indices, err_msg=f"rank {rank}: empty second shard")
+            np.testing.assert_array_equal(z[f"tiny_f{rep}"], tiny_want.fusion)
             for ci, w in enumerate(want):
                 np.testing.assert_array_equal(z[f"i{rep}_{ci}"], w.indices, err_msg=f"rank {rank} case {ci}")
                 np.testing.assert_array_equal(z[f"f{rep}_{ci}"], w.fusion)
