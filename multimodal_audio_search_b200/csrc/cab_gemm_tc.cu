@@ -138,6 +138,24 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// Packed fp32 pairs (FMUL2 / FFMA2) and the 3-input maximum (FMNMX3) of sm_100: the epilogue's
+// per-score work in a third of the issue slots -- under the 1 kW cap issue slots are clock.
+__device__ __forceinline__ uint64_t pack2(uint32_t lo, uint32_t hi) {
+    uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float r; asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r;
+}
+
 // K-major, 128-byte-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
 // start address >> 4 | LBO (16 B) | SBO = 8 rows x 128 B = 1024 | version 1 | SWIZZLE_128B.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
@@ -395,12 +413,26 @@ gemm_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 const float bound_f = key_score(bound);
                 uint32_t m = 0;                                                // bit j: column j may enter the list
                 float f[32];
+                bool any = true;
                 if (fast) {
-                    // branch-free: 4 independent instructions per score, full ILP across the 32 columns
+                    // branch-free, packed: f = wa * s_asr + wb * s_audio for two columns per instruction
+                    // (FMUL2 + FFMA2, bit-identical to the scalar form), then ONE maximum over the 32
+                    // columns (FMNMX3 tree) and one compare: almost every chunk ends here
+                    const uint64_t wa2 = pack2(__float_as_uint(w.wa), __float_as_uint(w.wa));
+                    const uint64_t wb2 = pack2(__float_as_uint(w.wb), __float_as_uint(w.wb));
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        f[j] = fmaf(w.wa, __uint_as_float(va[j]), w.wb * __uint_as_float(vb[j]));
-                        m |= f[j] >= bound_f ? (1u << j) : 0u;
+                    for (int j = 0; j < 32; j += 2)
+                        unpack2(fma2(wa2, pack2(va[j], va[j + 1]), mul2(wb2, pack2(vb[j], vb[j + 1]))), f[j], f[j + 1]);
+                    float mx[11];
+#pragma unroll
+                    for (int j = 0; j < 10; ++j) mx[j] = max3(f[3 * j], f[3 * j + 1], f[3 * j + 2]);
+                    mx[10] = fmaxf(f[30], f[31]);
+                    const float m0 = max3(mx[0], mx[1], mx[2]), m1 = max3(mx[3], mx[4], mx[5]), m2 = max3(mx[6], mx[7], mx[8]);
+                    const float top = max3(max3(m0, m1, m2), mx[9], mx[10]);
+                    any = __any_sync(kFull, top >= bound_f);
+                    if (any) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) m |= f[j] >= bound_f ? (1u << j) : 0u;
                     }
                 } else {
 #pragma unroll
@@ -413,7 +445,7 @@ gemm_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 // Rare survivors.  The loop runs over the union of the lanes' masks, so the column index
                 // is warp-uniform and the register pair is picked by a jump table (no divergence, no
                 // TMEM re-read); only the lanes that flagged the column push.
-                uint32_t um = __reduce_or_sync(kFull, m);
+                uint32_t um = any ? __reduce_or_sync(kFull, m) : 0u;
                 while (um) {
                     const int j = __ffs(um) - 1;
                     um &= um - 1;
