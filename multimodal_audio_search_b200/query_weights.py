@@ -13,8 +13,41 @@ from typing import Tuple
 from .keyword_table import ASR_KEYWORDS, AUDIO_KEYWORDS
 
 
+def _bucket(table):
+    """Keywords by their first two characters: a keyword can only occur in a query that contains
+    that bigram, so a query of n characters tests the few keywords behind its <= n-1 bigrams instead
+    of all 586 (one-character keywords, if any, are tested always)."""
+    by_bigram, short = {}, []
+    for kw, n in table.items():
+        if len(kw) >= 2:
+            by_bigram.setdefault(kw[:2], []).append((kw, n))
+        else:
+            short.append((kw, n))
+    return by_bigram, short
+
+
+_ASR_BUCKETS, _AUDIO_BUCKETS = _bucket(ASR_KEYWORDS), _bucket(AUDIO_KEYWORDS)
+
+
+def _count(query_lower: str, buckets) -> int:
+    by_bigram, short = buckets
+    total = sum(n for kw, n in short if kw in query_lower)
+    for bg in {query_lower[i:i + 2] for i in range(len(query_lower) - 1)}:
+        for kw, n in by_bigram.get(bg, ()):
+            if kw in query_lower:
+                total += n
+    return total
+
+
 def count_matches(query_lower: str) -> Tuple[int, int]:
-    """(asr_matches, audio_matches): every listed occurrence of a keyword counts (:586-587)."""
+    """(asr_matches, audio_matches): every listed occurrence of a keyword that is a substring of
+    the query counts (:586-587) -- `sum(n for kw, n in table.items() if kw in query)`, evaluated
+    through the bigram buckets."""
+    return _count(query_lower, _ASR_BUCKETS), _count(query_lower, _AUDIO_BUCKETS)
+
+
+def count_matches_plain(query_lower: str) -> Tuple[int, int]:
+    """The literal form (every keyword tested); kept as the cross-check of the bucketed one."""
     asr = sum(n for kw, n in ASR_KEYWORDS.items() if kw in query_lower)
     audio = sum(n for kw, n in AUDIO_KEYWORDS.items() if kw in query_lower)
     return asr, audio

@@ -137,7 +137,7 @@ class _TextColumn:
     def __getitem__(self, i: int) -> str:
         if i < self.n_base:
             lo, hi = int(self.offsets[i]), int(self.offsets[i + 1])
-            return bytes(self.blob[lo:hi]).decode("utf-8")
+            return bytes(self.blob[lo:hi]).decode("utf-8") if hi > lo else ""
         return self.tail[i - self.n_base]
 
     def consolidated(self):

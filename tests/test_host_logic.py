@@ -85,3 +85,19 @@ def test_synth_stress_distributions_have_the_advertised_shape():
         assert (unit(a) @ q[qi]).min() > 0.45 and (unit(b) @ q[qi]).min() > 0.45
         a, b, _, _ = synth.library(3, n, mode="clustered", rows=rows[cl != qi][:20000])
         assert np.abs(unit(a) @ q[qi]).max() < 0.3
+
+
+def test_bucketed_keyword_count_equals_the_literal_form():
+    """query_weights.count_matches goes through first-bigram buckets; it must equal the literal
+    `sum(n for kw in table if kw in query)` on the golden queries, on every keyword itself, on
+    concatenations and on random strings over the keywords' alphabet."""
+    from multimodal_audio_search_b200.keyword_table import ASR_KEYWORDS, AUDIO_KEYWORDS
+    rng = np.random.default_rng(0)
+    kws = list(ASR_KEYWORDS) + list(AUDIO_KEYWORDS)
+    alphabet = sorted(set("".join(kws)) | {" "})
+    cases = []
+    cases += kws + ["", "a", "xy"] + [kws[i] + kws[-i - 1] for i in range(0, len(kws), 7)]
+    cases += [" ".join(rng.choice(kws, 4)) for _ in range(200)]
+    cases += ["".join(rng.choice(alphabet, rng.integers(1, 40))) for _ in range(2000)]
+    for q in cases:
+        assert query_weights.count_matches(q) == query_weights.count_matches_plain(q), q
