@@ -239,6 +239,14 @@ CAB_API int cab_index_exchange_stamps(cab_index *idx, uint64_t *out, int max_row
  * "gemv_blocks_per_sm" (resident CTAs per SM, 0 = default), "gemv_query_tile" (queries scored per
  * corpus pass, 1/2/4, 0 = default 4), "gemv_batch", "gemm_min_queries",
  * "time_kernels", "sync_after_search", "stamp_exchange";
+ * "tensor_core_shadow" = 1 (fp32 index): keep bf16 shadow copies of both corpora (+50 % memory);
+ * cab_search batches of >= "gemm_min_queries" queries (k <= 112) are then PRE-selected on the
+ * tensor cores from the shadows (k + k/2 + 32 rows per query), re-scored exactly from the fp32
+ * rows, and certified per query: the top-k is provably the exact one when k re-scored candidates
+ * lie above (scan score of the worst selected row + 4e-3, the bound on the bf16 error of a cosine
+ * of unit vectors).  Uncertified queries are re-run on the exact GEMV scan before the call
+ * returns (get_option "last_uncertified" / "total_uncertified" / "total_shadow_queries"), so the
+ * results are the fp32 path's; with device outputs the call synchronises the stream once.
  * "raw_dot" = 1: similarities are raw dot products <query, row> of the vectors AS APPENDED instead
  * of cosines (the index keeps every row's original length; the query is not normalised) -- the
  * ranking rule of the reference's earlier engine, previous_iterations/clean_audio_search.py:306-310

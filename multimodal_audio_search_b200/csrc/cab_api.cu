@@ -38,6 +38,12 @@ struct cab_index {
     int64_t capacity = 0, size = 0, row_base = 0;
     void *asr = nullptr, *audio = nullptr;
     float *norm_asr = nullptr, *norm_audio = nullptr;   // original row lengths (raw dot-product scoring)
+    // fp32 index, option tensor_core_shadow: bf16 copies of both corpora -- batches are PRE-selected on
+    // the tensor cores from the shadows, re-scored exactly from the fp32 rows and certified per query
+    void *shadow_asr = nullptr, *shadow_audio = nullptr;
+    uint8_t *d_cert = nullptr;     size_t sz_cert = 0;    // per query of the last shadow batch: 1 = provably exact
+    int cert_pending = 0;                                // queries of the batch whose certificates are to be checked
+    int64_t last_uncertified = 0, total_uncertified = 0, total_shadow_queries = 0;
     uint8_t *flags = nullptr;
     cudaStream_t own_stream = nullptr;
     // search workspace (device)
@@ -159,15 +165,19 @@ static int grow(cab_index *idx, int64_t new_cap) {
     const size_t row_bytes = CAB_DIM * elem_size(idx->dtype);
     void *na = nullptr, *nb = nullptr;
     float *la = nullptr, *lb = nullptr;
+    void *sa_ = nullptr, *sb_ = nullptr;
+    const bool shadow = idx->shadow_asr != nullptr;
     uint8_t *nf = nullptr;
     CU(idx, cudaSetDevice(idx->device));
     cudaError_t e = cudaMalloc(&na, size_t(new_cap) * row_bytes);
     if (e == cudaSuccess) e = cudaMalloc(&nb, size_t(new_cap) * row_bytes);
     if (e == cudaSuccess) e = cudaMalloc((void **)&la, size_t(new_cap) * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc((void **)&lb, size_t(new_cap) * sizeof(float));
+    if (e == cudaSuccess && shadow) e = cudaMalloc(&sa_, size_t(new_cap) * CAB_DIM * 2);
+    if (e == cudaSuccess && shadow) e = cudaMalloc(&sb_, size_t(new_cap) * CAB_DIM * 2);
     if (e == cudaSuccess) e = cudaMalloc(&nf, align_up(size_t(new_cap), 16));     // the tensor-core epilogue reads flag WORDS
     if (e != cudaSuccess) {
-        cudaFree(na); cudaFree(nb); cudaFree(nf); cudaFree(la); cudaFree(lb); cudaGetLastError();
+        cudaFree(na); cudaFree(nb); cudaFree(nf); cudaFree(la); cudaFree(lb); cudaFree(sa_); cudaFree(sb_); cudaGetLastError();
         return fail(idx, CAB_ERR_NOMEM, "cannot allocate %lld rows (%s)", (long long)new_cap, cudaGetErrorString(e));
     }
     if (idx->size > 0) {
@@ -176,10 +186,16 @@ static int grow(cab_index *idx, int64_t new_cap) {
         CU(idx, cudaMemcpyAsync(nf, idx->flags, size_t(idx->size), cudaMemcpyDeviceToDevice, idx->own_stream));
         CU(idx, cudaMemcpyAsync(la, idx->norm_asr, size_t(idx->size) * sizeof(float), cudaMemcpyDeviceToDevice, idx->own_stream));
         CU(idx, cudaMemcpyAsync(lb, idx->norm_audio, size_t(idx->size) * sizeof(float), cudaMemcpyDeviceToDevice, idx->own_stream));
+        if (shadow) {
+            CU(idx, cudaMemcpyAsync(sa_, idx->shadow_asr, size_t(idx->size) * CAB_DIM * 2, cudaMemcpyDeviceToDevice, idx->own_stream));
+            CU(idx, cudaMemcpyAsync(sb_, idx->shadow_audio, size_t(idx->size) * CAB_DIM * 2, cudaMemcpyDeviceToDevice, idx->own_stream));
+        }
     }
     CU(idx, cudaStreamSynchronize(idx->own_stream));
     cudaFree(idx->asr); cudaFree(idx->audio); cudaFree(idx->flags); cudaFree(idx->norm_asr); cudaFree(idx->norm_audio);
+    cudaFree(idx->shadow_asr); cudaFree(idx->shadow_audio);
     idx->asr = na; idx->audio = nb; idx->flags = nf; idx->norm_asr = la; idx->norm_audio = lb; idx->capacity = new_cap;
+    idx->shadow_asr = sa_; idx->shadow_audio = sb_;
     return CAB_OK;
 }
 
@@ -230,6 +246,7 @@ int cab_index_destroy(cab_index *idx) {
     cudaSetDevice(idx->device);
     if (idx->own_stream) cudaStreamSynchronize(idx->own_stream);
     cudaFree(idx->asr); cudaFree(idx->audio); cudaFree(idx->flags); cudaFree(idx->norm_asr); cudaFree(idx->norm_audio);
+    cudaFree(idx->shadow_asr); cudaFree(idx->shadow_audio); cudaFree(idx->d_cert);
     cudaFree(idx->d_params);
     cudaFree(idx->d_partial_keys); cudaFree(idx->d_cands);
     cudaFree(idx->d_out); cudaFree(idx->d_gemm_ws); cudaFree(idx->d_nonfinite); cudaFree(idx->d_rows); cudaFree(idx->d_counters); cudaFree(idx->d_scores);
@@ -300,8 +317,8 @@ int cab_index_append(cab_index *idx, const float *asr_rows, const float *audio_r
     }
     const int64_t dst0 = idx->size;
     if (rows_loc == CAB_DEVICE) {
-        launch_normalize_rows(asr_rows, idx->asr, idx->dtype, dst0, n_rows, idx->d_nonfinite, idx->norm_asr, s);
-        launch_normalize_rows(audio_rows, idx->audio, idx->dtype, dst0, n_rows, idx->d_nonfinite, idx->norm_audio, s);
+        launch_normalize_rows(asr_rows, idx->asr, idx->dtype, dst0, n_rows, idx->d_nonfinite, idx->norm_asr, idx->shadow_asr, s);
+        launch_normalize_rows(audio_rows, idx->audio, idx->dtype, dst0, n_rows, idx->d_nonfinite, idx->norm_audio, idx->shadow_audio, s);
         idx->launches += 2;
         if (flags) CU(idx, cudaMemcpyAsync(idx->flags + dst0, flags, size_t(n_rows), cudaMemcpyDeviceToDevice, s));
         else CU(idx, cudaMemsetAsync(idx->flags + dst0, 3, size_t(n_rows), s));
@@ -329,8 +346,8 @@ int cab_index_append(cab_index *idx, const float *asr_rows, const float *audio_r
             if (step >= 2) CU(idx, cudaEventSynchronize(idx->ev_slot[slot]));     // the slot's previous chunk is consumed
             if (asr_rows) { memcpy(ha, asr_rows + r * CAB_DIM, size_t(m) * row_bytes); CU(idx, cudaMemcpyAsync(da, ha, size_t(m) * row_bytes, cudaMemcpyHostToDevice, s)); }
             if (audio_rows) { memcpy(hb, audio_rows + r * CAB_DIM, size_t(m) * row_bytes); CU(idx, cudaMemcpyAsync(db, hb, size_t(m) * row_bytes, cudaMemcpyHostToDevice, s)); }
-            launch_normalize_rows(asr_rows ? da : nullptr, idx->asr, idx->dtype, dst0 + r, m, idx->d_nonfinite, idx->norm_asr, s);
-            launch_normalize_rows(audio_rows ? db : nullptr, idx->audio, idx->dtype, dst0 + r, m, idx->d_nonfinite, idx->norm_audio, s);
+            launch_normalize_rows(asr_rows ? da : nullptr, idx->asr, idx->dtype, dst0 + r, m, idx->d_nonfinite, idx->norm_asr, idx->shadow_asr, s);
+            launch_normalize_rows(audio_rows ? db : nullptr, idx->audio, idx->dtype, dst0 + r, m, idx->d_nonfinite, idx->norm_audio, idx->shadow_audio, s);
             idx->launches += 2;
             CU(idx, cudaEventRecord(idx->ev_slot[slot], s));
         }
@@ -406,7 +423,8 @@ int cab_index_append_synth(cab_index *idx, uint32_t seed, int64_t n_total, int64
         for (int64_t r = 0; r < n_rows; r += chunk) {
             const int64_t m = std::min(chunk, n_rows - r);
             launch_synth_rows(p, st, partial ? 1 : 0, r0 + r, m, idx->d_rows, s);
-            launch_normalize_rows(idx->d_rows, dst, idx->dtype, idx->size + r, m, idx->d_nonfinite, st == 0 ? idx->norm_asr : idx->norm_audio, s);
+            launch_normalize_rows(idx->d_rows, dst, idx->dtype, idx->size + r, m, idx->d_nonfinite, st == 0 ? idx->norm_asr : idx->norm_audio,
+                                  st == 0 ? idx->shadow_asr : idx->shadow_audio, s);
             idx->launches += 2;
         }
     }
@@ -763,21 +781,35 @@ static int run_local(cab_index *idx, const float *queries, int queries_loc, cons
             return fail(idx, CAB_ERR_INVALID, "weights must be finite and >= 0");
     for (int i = 0; i < nq; ++i)
         if (!(w_asr[i] + w_audio[i] > 0)) return fail(idx, CAB_ERR_INVALID, "w_asr + w_audio must be > 0 for every query");
+    // fp32 library with bf16 shadows: the tensor cores PRE-select k_sel > k rows per query from the
+    // shadows, the finalize kernel re-scores them exactly from the fp32 rows and certifies each query
+    // (FinalizeArgs::cert_out); only a plain cab_search takes this route (the caller of run_local
+    // re-runs uncertified queries on the exact scan).
+    const int k_sel_shadow = std::min(CAB_MAX_K, k + k / 2 + 32);
+    const bool shadow_ok = idx->dtype == CAB_F32 && idx->shadow_asr && out && !sh && !cand_dst && !idx->opt_raw_dot &&
+                           k_sel_shadow >= k + 16 && idx->size > 0;
     bool use_gemm = false;
     if (path == CAB_PATH_GEMM) {
-        if (idx->dtype != CAB_BF16) return fail(idx, CAB_ERR_INVALID, "the tensor-core path needs a bf16 index");
+        if (idx->dtype != CAB_BF16 && !shadow_ok)
+            return fail(idx, CAB_ERR_INVALID, "the tensor-core path needs a bf16 index (or an fp32 index with option tensor_core_shadow, "
+                                              "k <= 112, through cab_search)");
         if (idx->opt_raw_dot) return fail(idx, CAB_ERR_INVALID, "raw dot-product scoring (option raw_dot) is served by the GEMV path only");
         if (!gemm_path_available()) return fail(idx, CAB_ERR_INVALID, "tensor-core path not built");
         use_gemm = true;
     } else if (path == CAB_PATH_AUTO) {
-        use_gemm = idx->dtype == CAB_BF16 && nq >= idx->opt_gemm_min_queries && gemm_path_available() && !idx->opt_raw_dot;
+        use_gemm = (idx->dtype == CAB_BF16 || shadow_ok) && nq >= idx->opt_gemm_min_queries && gemm_path_available() && !idx->opt_raw_dot;
     }
+    const bool certified = use_gemm && idx->dtype == CAB_F32;
+    const int k_sel = certified ? k_sel_shadow : k;                // rows selected by the scan per query
+    constexpr float kShadowEps = 4.0e-3f;                          // >= 2^-8 + 2^-18: |bf16 x bf16 cosine - fp32 cosine| of unit vectors
     CU(idx, cudaSetDevice(idx->device));
     const int n_partials = use_gemm ? gemm_partials_per_query(idx->sm_count) : gemv_max_grid(idx->sm_count);
     const int batch = use_gemm ? std::min(nq, kGemmQueriesPerPass) : int(std::min<int64_t>(nq, idx->opt_gemv_batch));
-    int rc = ensure_workspace(idx, nq, k, n_partials, use_gemm ? kGemmQueriesPerPass : batch,
-                              use_gemm ? kGemmListCap : k, use_gemm ? gemm_workspace_bytes(nq, k, idx->sm_count) : 0);
+    int rc = ensure_workspace(idx, nq, k_sel, n_partials, use_gemm ? kGemmQueriesPerPass : batch,
+                              use_gemm ? kGemmListCap : k, use_gemm ? gemm_workspace_bytes(nq, k_sel, idx->sm_count) : 0);
     if (rc != CAB_OK) return rc;
+    if (certified && (rc = ensure_dev(idx, &idx->d_cert, &idx->sz_cert, size_t(nq)))) return rc;
+    idx->cert_pending = certified ? nq : 0;
     // One query: parameters travel in the kernel arguments, no H2D copy ahead of the scan.
     InlineParams inl{};
     const float *dq = nullptr;
@@ -823,8 +855,12 @@ static int run_local(cab_index *idx, const float *queries, int queries_loc, cons
     ScanArgs sa{};
     sa.asr = idx->asr; sa.audio = idx->audio; sa.flags = idx->flags; sa.n_rows = idx->size;
     if (idx->opt_raw_dot) { sa.norm_asr = idx->norm_asr; sa.norm_audio = idx->norm_audio; }
-    sa.dtype = idx->dtype; sa.k = k;
+    sa.dtype = idx->dtype; sa.k = k_sel;
     sa.select_threshold = float(threshold) - 1e-6f;
+    if (certified) {                                   // scan the shadows; nothing above (threshold - eps) may be missed
+        sa.asr = idx->shadow_asr; sa.audio = idx->shadow_audio; sa.dtype = CAB_BF16;
+        sa.select_threshold = float(threshold) - kShadowEps - 1e-6f;
+    }
     sa.partial_keys = idx->d_partial_keys;
     sa.inl = inl;
     // A device query may have been written by the kernel right in front of the scan on the caller's
@@ -837,7 +873,8 @@ static int run_local(cab_index *idx, const float *queries, int queries_loc, cons
     fa.inl = inl;
     fa.asr = idx->asr; fa.audio = idx->audio; fa.flags = idx->flags; fa.dtype = idx->dtype;
     fa.norm_asr = sa.norm_asr; fa.norm_audio = sa.norm_audio;
-    fa.row_base = idx->row_base; fa.k = k; fa.partial_keys = idx->d_partial_keys;
+    fa.row_base = idx->row_base; fa.k = k_sel; fa.partial_keys = idx->d_partial_keys;
+    if (certified) fa.cert_eps = kShadowEps;
     fa.n_partials = n_partials; fa.force_general = int(idx->opt_finalize_general);
     fa.slot_stride = use_gemm ? kGemmListCap : k;
     fa.work_counters = use_gemm ? nullptr : idx->d_counters;
@@ -860,7 +897,8 @@ static int run_local(cab_index *idx, const float *queries, int queries_loc, cons
             launch_gemv_scan(sa, plan, s);
         }
         if (idx->opt_time_kernels && q0 + batch >= nq) CU(idx, cudaEventRecord(idx->ev_t1, s));
-        fa.queries = sa.queries; fa.n_queries = m; fa.cands = peer ? nullptr : cands + size_t(q0) * k;
+        fa.queries = sa.queries; fa.n_queries = m; fa.cands = peer ? nullptr : cands + size_t(q0) * k_sel;
+        if (certified) fa.cert_out = idx->d_cert + q0;
         if (peer) { fa.peer = *peer; fa.peer.q0 = q0; fa.peer.signal = q0 + batch >= nq ? 1 : 0; }
         if (emit_here) {
             EmitArgs eb = ea;                           // this batch's slice of the outputs
@@ -918,6 +956,37 @@ static int finish_outputs(cab_index *idx, int nq, int k, const UserOut &o, cudaS
     return CAB_OK;
 }
 
+// Shadow path (fp32 library, tensor-core preselection): read the per-query certificates of the batch
+// that just ran and re-run every query that is not provably exact on the exact scan, into the same
+// output slots.  Few of them: one by one; more than a quarter of the batch: the whole batch.
+static int rerun_uncertified(cab_index *idx, const float *queries, int queries_loc, const double *w_asr,
+                             const double *w_audio, int k, double threshold, const UserOut &o, cudaStream_t s) {
+    const int nq = idx->cert_pending;
+    idx->cert_pending = 0;
+    std::vector<uint8_t> cert(size_t(nq), 1);
+    CU(idx, cudaMemcpyAsync(cert.data(), idx->d_cert, size_t(nq), cudaMemcpyDeviceToHost, s));
+    CU(idx, cudaStreamSynchronize(s));
+    int bad = 0;
+    for (uint8_t c : cert) bad += c == 0;
+    idx->last_uncertified = bad; idx->total_uncertified += bad; idx->total_shadow_queries += nq;
+    if (bad == 0) return CAB_OK;
+    int rc;
+    if (bad * 4 > nq) {
+        if ((rc = run_local(idx, queries, queries_loc, w_asr, w_audio, nq, k, threshold, CAB_PATH_GEMV, &o, nullptr, nullptr, s))) return rc;
+        return finish_outputs(idx, nq, k, o, s);
+    }
+    for (int i = 0; i < nq; ++i) {
+        if (cert[size_t(i)]) continue;
+        const size_t off = size_t(i) * k;
+        const UserOut oi{o.index ? o.index + off : nullptr, o.fusion ? o.fusion + off : nullptr, o.asr ? o.asr + off : nullptr,
+                         o.audio ? o.audio + off : nullptr, o.flags ? o.flags + off : nullptr, o.count ? o.count + i : nullptr, o.loc};
+        if ((rc = run_local(idx, queries + size_t(i) * CAB_DIM, queries_loc, w_asr + i, w_audio + i, 1, k, threshold, CAB_PATH_GEMV,
+                            &oi, nullptr, nullptr, s))) return rc;
+        if ((rc = finish_outputs(idx, 1, k, oi, s))) return rc;
+    }
+    return CAB_OK;
+}
+
 int cab_search(cab_index *idx, const float *queries, int queries_loc, const double *w_asr,
                const double *w_audio, int n_queries, int k, double threshold, int path,
                int64_t *out_index, double *out_fusion, float *out_asr, float *out_audio,
@@ -929,7 +998,9 @@ int cab_search(cab_index *idx, const float *queries, int queries_loc, const doub
     if (rc != CAB_OK) return rc;
     rc = run_local(idx, queries, queries_loc, w_asr, w_audio, n_queries, k, threshold, path, &o, nullptr, nullptr, s);
     if (rc != CAB_OK) return rc;
-    return finish_outputs(idx, n_queries, k, o, s);
+    if ((rc = finish_outputs(idx, n_queries, k, o, s)) != CAB_OK) { idx->cert_pending = 0; return rc; }
+    if (idx->cert_pending) return rerun_uncertified(idx, queries, queries_loc, w_asr, w_audio, k, threshold, o, s);
+    return CAB_OK;
 }
 
 int cab_search_candidates(cab_index *idx, const float *queries, int queries_loc,
@@ -1182,6 +1253,28 @@ int cab_index_set_option(cab_index *idx, const char *key, int64_t value) {
     else if (k == "finalize_general") idx->opt_finalize_general = value != 0;
     else if (k == "queries_settled") idx->opt_queries_settled = value != 0;
     else if (k == "raw_dot") idx->opt_raw_dot = value != 0;
+    else if (k == "tensor_core_shadow") {
+        if (idx->dtype != CAB_F32) return fail(idx, CAB_ERR_INVALID, "tensor_core_shadow is for fp32 indices (a bf16 index is its own tensor-core operand)");
+        CU(idx, cudaSetDevice(idx->device));
+        CU(idx, cudaDeviceSynchronize());
+        if (value && !idx->shadow_asr) {
+            const size_t bytes = size_t(std::max<int64_t>(idx->capacity, 1)) * CAB_DIM * 2;
+            cudaError_t e = cudaMalloc(&idx->shadow_asr, bytes);
+            if (e == cudaSuccess) e = cudaMalloc(&idx->shadow_audio, bytes);
+            if (e != cudaSuccess) {
+                cudaFree(idx->shadow_asr); idx->shadow_asr = idx->shadow_audio = nullptr; cudaGetLastError();
+                return fail(idx, CAB_ERR_NOMEM, "cannot allocate the bf16 shadows (%s)", cudaGetErrorString(e));
+            }
+            launch_shadow_rows(static_cast<const float *>(idx->asr), idx->shadow_asr, 0, idx->size, idx->own_stream);
+            launch_shadow_rows(static_cast<const float *>(idx->audio), idx->shadow_audio, 0, idx->size, idx->own_stream);
+            idx->launches += 2;
+            CU(idx, cudaGetLastError());
+            CU(idx, cudaStreamSynchronize(idx->own_stream));
+        } else if (!value && idx->shadow_asr) {
+            cudaFree(idx->shadow_asr); cudaFree(idx->shadow_audio);
+            idx->shadow_asr = idx->shadow_audio = nullptr;
+        }
+    }
     else if (k == "stamp_exchange") { idx->opt_stamp_exchange = value != 0; idx->stamp_calls = 0; }
     else if (k == "gemv_chunk_rows") { if (value < 0 || value > 4096) return fail(idx, CAB_ERR_INVALID, "gemv_chunk_rows in 0..4096 (0 = auto)"); idx->opt_chunk_rows = value; }
     else if (k == "gemm_min_queries") { if (value < 1) return fail(idx, CAB_ERR_INVALID, "gemm_min_queries >= 1"); idx->opt_gemm_min_queries = value; }
@@ -1201,6 +1294,10 @@ int64_t cab_index_get_option(const cab_index *idx, const char *key) {
     if (k == "finalize_general") return idx->opt_finalize_general;
     if (k == "queries_settled") return idx->opt_queries_settled;
     if (k == "raw_dot") return idx->opt_raw_dot;
+    if (k == "tensor_core_shadow") return idx->shadow_asr != nullptr;
+    if (k == "last_uncertified") return idx->last_uncertified;
+    if (k == "total_uncertified") return idx->total_uncertified;
+    if (k == "total_shadow_queries") return idx->total_shadow_queries;
     if (k == "stamp_exchange") return idx->opt_stamp_exchange;
     if (k == "gemv_chunk_rows") return idx->opt_chunk_rows;
     if (k == "gemm_min_queries") return idx->opt_gemm_min_queries;

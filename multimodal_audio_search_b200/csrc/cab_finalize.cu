@@ -484,6 +484,8 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, E
         trim();
     }
     int n_win = s_cnt;
+    // scan score below which rows were NOT selected (certificate of the shadow path, see FinalizeArgs)
+    const float cert_cutoff = (a.cert_out && n_win == a.k) ? key_score(s_sort[a.k - 1]) : a.select_threshold;
     if (stamp) e.stamps[1] = globaltimer_ns();
 
     // Everything the next scan on this stream touches -- its ticket counters (reset above), the
@@ -557,6 +559,12 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, E
 
     // ---- fused emit (single candidate list) ------------------------------------------------------------
     emit_ranked([&](int t) { return s_cand[t]; }, a.k, qi, e, !finite, score, index, pos);
+    if (a.cert_out) {                  // a.k <= 256: emit_ranked left score[t] = orderable float64 fusion of candidate t
+        const double line = double(cert_cutoff) + double(a.cert_eps);
+        const int t = threadIdx.x;
+        const int n_safe = __syncthreads_count(t < a.k && score[t] != 0ull && unorderable64(score[t]) > line);
+        if (t == 0) a.cert_out[qi] = (n_safe >= e.k || line <= e.threshold || !finite) ? 1 : 0;
+    }
     host_signal(e);
 }
 

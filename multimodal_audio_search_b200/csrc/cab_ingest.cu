@@ -14,7 +14,8 @@ __global__ void __launch_bounds__(256) normalize_rows_kernel(const float *__rest
                                                              void *__restrict__ dst,
                                                              int64_t dst_row, int64_t n,
                                                              int *__restrict__ nonfinite,
-                                                             float *__restrict__ norms) {
+                                                             float *__restrict__ norms,
+                                                             __nv_bfloat16 *__restrict__ shadow) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
@@ -47,20 +48,43 @@ __global__ void __launch_bounds__(256) normalize_rows_kernel(const float *__rest
                 reinterpret_cast<uint2 *>(reinterpret_cast<__nv_bfloat16 *>(dst) + out_row * kDim)[lane + 32 * j] = pk;
             } else {
                 reinterpret_cast<float4 *>(reinterpret_cast<float *>(dst) + out_row * kDim)[lane + 32 * j] = o4;
+                if (shadow) {                          // bf16 copy of an fp32 library for the tensor-core preselection
+                    __nv_bfloat162 lo = __floats2bfloat162_rn(o4.x, o4.y);
+                    __nv_bfloat162 hi = __floats2bfloat162_rn(o4.z, o4.w);
+                    uint2 pk = make_uint2(*reinterpret_cast<uint32_t *>(&lo), *reinterpret_cast<uint32_t *>(&hi));
+                    reinterpret_cast<uint2 *>(shadow + out_row * kDim)[lane + 32 * j] = pk;
+                }
             }
         }
     }
 }
 
 void launch_normalize_rows(const float *src, void *dst, int dtype, int64_t dst_row, int64_t n,
-                           int *nonfinite, float *norms, cudaStream_t s) {
+                           int *nonfinite, float *norms, void *shadow, cudaStream_t s) {
     if (n <= 0) return;
     int64_t blocks = (n + 7) / 8;
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (dtype == CAB_BF16)
-        normalize_rows_kernel<true><<<int(blocks), 256, 0, s>>>(src, dst, dst_row, n, nonfinite, norms);
+        normalize_rows_kernel<true><<<int(blocks), 256, 0, s>>>(src, dst, dst_row, n, nonfinite, norms, nullptr);
     else
-        normalize_rows_kernel<false><<<int(blocks), 256, 0, s>>>(src, dst, dst_row, n, nonfinite, norms);
+        normalize_rows_kernel<false><<<int(blocks), 256, 0, s>>>(src, dst, dst_row, n, nonfinite, norms,
+                                                                  static_cast<__nv_bfloat16 *>(shadow));
+}
+
+// ---- bf16 shadow of stored fp32 rows (option tensor_core_shadow switched on after the rows) --------
+__global__ void shadow_rows_kernel(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst, int64_t n_elems) {
+    int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+    for (; i < n_elems; i += int64_t(gridDim.x) * blockDim.x * 4) {
+        const float4 v = *reinterpret_cast<const float4 *>(src + i);
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+        *reinterpret_cast<uint2 *>(dst + i) = make_uint2(*reinterpret_cast<uint32_t *>(&lo), *reinterpret_cast<uint32_t *>(&hi));
+    }
+}
+void launch_shadow_rows(const float *src, void *dst, int64_t r0, int64_t n, cudaStream_t s) {
+    if (n <= 0) return;
+    int64_t blocks = (n * kDim / 4 + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    shadow_rows_kernel<<<int(blocks), 256, 0, s>>>(src + r0 * kDim, static_cast<__nv_bfloat16 *>(dst) + r0 * kDim, n * kDim);
 }
 
 // ---- read back ---------------------------------------------------------------------------------

@@ -22,8 +22,11 @@ struct PerDeviceOnce {
 // Normalise n raw fp32 rows (sklearn `normalize` semantics) into the store at row offset `dst_row`.
 // src == nullptr writes zero rows.  *nonfinite (device int) is set to 1 if any value is NaN/Inf.
 // norms[dst_row + i] receives the length of raw row i (0 for a zero / missing row).
+// shadow (fp32 stores only, may be null): a bf16 copy of the normalised rows, same row offsets.
 void launch_normalize_rows(const float *src, void *dst, int dtype, int64_t dst_row, int64_t n,
-                           int *nonfinite, float *norms, cudaStream_t s);
+                           int *nonfinite, float *norms, void *shadow, cudaStream_t s);
+// bf16 shadow of rows [r0, r0 + n) of an fp32 store that is already normalised.
+void launch_shadow_rows(const float *src, void *dst, int64_t r0, int64_t n, cudaStream_t s);
 // Deterministic synthetic rows (synth.py) for global rows [r0, r1) of stream 0/1, raw fp32.
 struct SynthParams {
     uint32_t seed;
@@ -169,6 +172,13 @@ struct FinalizeArgs {
     const int32_t *levels;
     float select_threshold;
     float level_step;
+    // fp32 library searched through its bf16 shadow (tensor-core PRE-selection of k > e.k rows, then
+    // this kernel's exact fp32 re-score): cert_out[q] = 1 iff the emitted top-e.k is provably the
+    // exact one -- at least e.k re-scored candidates lie above (score of the worst selected row in
+    // the scan + cert_eps), the line no unselected row can reach -- else 0 and the host re-runs that
+    // query on the exact scan.  Null = plain search.
+    uint8_t *cert_out;
+    float cert_eps;                // bound on |bf16 scan score - exact score|
     PeerPush peer;
     InlineParams inl;
 };

@@ -135,6 +135,14 @@ class SegmentIndex:
         N.check(self._lib.cab_peer_snapshot(self._h, _ptr(out), out.size, None), self._h)
         return out
 
+    def enable_tensor_core_batches(self, on: bool = True):
+        """fp32 index only: keep bf16 shadow copies of both corpora (+50 % HBM) so that batches of
+        >= 64 queries are PRE-selected on the tensor cores, re-scored exactly from the fp32 rows and
+        certified per query; a query whose top-k is not provably exact is re-run on the exact scan
+        (`get_option("last_uncertified")` says how many of the last batch).  Results are those of
+        the fp32 GEMV path; throughput is the bf16 tensor-core path's."""
+        self.set_option("tensor_core_shadow", int(bool(on)))
+
     def exchange_stamps(self, max_rows: int = 64) -> np.ndarray:
         """Option "stamp_exchange": uint64 [n, 6] %globaltimer ns of the last sharded searches --
         {scan complete, best k selected, winners re-scored, own flag raised, all ranks' flags seen,

@@ -358,3 +358,65 @@ def test_alternating_device_and_host_calls_on_one_handle():
         np.testing.assert_array_equal(dev.indices.cpu().numpy(), want_a.indices)
         np.testing.assert_array_equal(dev2.indices.cpu().numpy(), want_a.indices)
     idx.close()
+
+
+def test_fp32_batches_on_tensor_cores_with_exactness_certificates():
+    """fp32 library + bf16 shadows: batches are preselected on the tensor cores, re-scored exactly and
+    certified per query; uncertified queries are re-run on the exact scan.  The answer must be the
+    fp32 GEMV path's (same re-score code, float64 fusion), for planted data (everything certified),
+    for dense threshold-level noise at k = 100 (certificates fail, re-runs one by one and as a whole
+    batch), host and device outputs, and after the store has grown."""
+    torch = pytest.importorskip("torch")
+    seed, n, nq = 61, 300_000, 96
+    idx = SegmentIndex("fp32", capacity=150_000)
+    idx.append_synth(seed, n, 0, 150_000, n_queries=nq, plants=30, partial=True)
+    idx.enable_tensor_core_batches()
+    idx.append_synth(seed, n, 150_000, n, n_queries=nq, plants=30, partial=True)      # grows the shadows too
+    q = synth.raw_queries(seed, 0, nq)
+    qd = torch.from_numpy(q).cuda()
+    wa = np.linspace(0.2, 0.8, nq); wb = 1 - wa
+    a, b, f, _ = synth.library(seed, n, nq, 30, True)
+
+    def same(x, y, what):
+        xi = x.indices.cpu().numpy() if hasattr(x.indices, "cpu") else x.indices
+        xf = x.fusion.cpu().numpy() if hasattr(x.fusion, "cpu") else x.fusion
+        bad = [i for i in range(len(xi)) if not (np.array_equal(xi[i], y.indices[i]) and np.array_equal(xf[i], y.fusion[i]))]
+        for i in bad:                                  # only swaps between rows closer than the fp32 tolerance are allowed
+            sx = dict(zip(xi[i].tolist(), xf[i].tolist())); sy = dict(zip(y.indices[i].tolist(), y.fusion[i].tolist()))
+            kth = min(min(sx.values()), min(sy.values()))
+            for r in set(sx) ^ set(sy):
+                assert abs(sx.get(r, sy.get(r)) - kth) <= FP32_TOL, (what, i, r)
+        return len(bad)
+
+    exact10 = idx.search(q, wa, wb, k=10, path="gemv")
+    l0 = idx.launch_count
+    got = idx.search(q, wa, wb, k=10)                              # auto: >= 64 queries -> tensor-core preselection
+    assert idx.get_option("total_shadow_queries") == nq and idx.get_option("last_uncertified") == 0
+    assert same(got, exact10, "planted k=10") == 0
+    assert idx.launch_count - l0 == 3                                # prologue + tensor-core scan + finalize
+    for qi in (0, 17, 95):
+        o = no.search(q[qi], a, b, f, wa[qi], wb[qi], k=10)
+        gi, gf, _, _, _ = result_row(got, qi)
+        assert_topk_matches(gi, gf, o, FP32_TOL)
+    dev = idx.search(qd, wa, wb, k=10, path="gemm")
+    assert same(dev, exact10, "planted k=10 device") == 0
+    # k = 100 on a library with 30 plants per query: ranks 31..100 are threshold-level noise rows,
+    # dense in score -> the certificate (100 candidates above the 128th scan score + 4e-3) fails
+    exact100 = idx.search(q, wa, wb, k=100, path="gemv")
+    got100 = idx.search(q, wa, wb, k=100)
+    n_rerun = idx.get_option("last_uncertified")
+    assert n_rerun > 0
+    same(got100, exact100, "dense k=100")
+    dev100 = idx.search(qd, wa, wb, k=100, path="gemm")
+    same(dev100, exact100, "dense k=100 device")
+    # a few uncertified queries in a certified batch: mix planted k=10 queries with ... threshold 0.05 makes more rows compete
+    low = idx.search(q, wa, wb, k=40, threshold=0.12)
+    exact_low = idx.search(q, wa, wb, k=40, threshold=0.12, path="gemv")
+    same(low, exact_low, "k=40")
+    assert idx.get_option("total_shadow_queries") >= 5 * nq
+    with pytest.raises(Exception, match="fp32"):
+        SegmentIndex("bf16").set_option("tensor_core_shadow", 1)
+    idx.enable_tensor_core_batches(False)
+    with pytest.raises(Exception, match="bf16 index"):
+        idx.search(q, wa, wb, k=10, path="gemm")
+    idx.close()
