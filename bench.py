@@ -54,6 +54,8 @@ WORKLOADS = {
     "10m_bf16_q1_top10": (10_000_000, "bf16", 1, 10, "gemv", "planted"),
     "10m_bf16_q256_top100": (10_000_000, "bf16", 256, 100, "gemm", "planted"),
     "12m5_bf16_q1_top100": (12_500_000, "bf16", 1, 100, "gemv", "planted"),     # 100M over 8 GPUs
+    # fp32 library, batches preselected on the tensor cores from bf16 shadows, exact fp32 re-score + certificate
+    "10m_fp32_q256_top10_tc": (10_000_000, "fp32", 256, 10, "gemm", "planted"),
     # pruning worst cases: every row beats the running k-th best /
     # many rows above the threshold
     "10m_fp32_q1_top10_ascending": (10_000_000, "fp32", 1, 10, "gemv", "ascending"),
@@ -339,6 +341,9 @@ def main():
         n_steps = steps + args.warmup
         n_plant_queries = min(n_steps * nq, 4096)
         idx = SegmentIndex(dtype, capacity=n_rows, device=local)
+        shadow = dtype == "fp32" and path == "gemm"
+        if shadow:
+            idx.enable_tensor_core_batches()
         for kv in args.option:
             key, v = kv.split("=")
             idx.set_option(key, int(v))
@@ -488,7 +493,8 @@ def main():
         out = None
         if rank == 0:
             norm = n_total / 1e6
-            alg_bytes = n_rows * bytes_per_row(dtype)            # one rank's scan reads its shard once per launch
+            # one rank's scan reads its shard once per launch (the bf16 shadows on the fp32 tensor-core route)
+            alg_bytes = n_rows * bytes_per_row("bf16" if shadow else dtype)
             if path == "gemm":
                 flops = nq * n_rows * 4 * 384
                 achieved = flops / (scan_ms * 1e-3) / 1e12
@@ -519,7 +525,8 @@ def main():
                 "metric": METRIC, "value": nq * 1e3 / ms_step * norm, "unit": UNIT, "n_gpus": world, "steps": steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None,
-                "dtype": "f32" if dtype == "fp32" else "bf16 storage, f32 accumulate",
+                "dtype": ("f32 (bf16 tensor-core preselection, exact f32 re-score)" if shadow else "f32") if dtype == "fp32"
+                         else "bf16 storage, f32 accumulate",
                 "data": "synthetic (integer-hash rows, %s); the reference arm uses isotropic unit rows of the same shape" % (
                     "planted neighbours" if mode == "planted" else mode),
                 "config": workload_config(name, world, args.threshold),
@@ -542,6 +549,18 @@ def main():
             }
             if breakdown:
                 out["exchange_breakdown"] = breakdown
+            if shadow:
+                t0 = time.perf_counter()
+                for i in range(2):
+                    sl = slice((args.warmup + i) * nq, (args.warmup + i + 1) * nq)
+                    exact = idx.search(q_dev[sl], wa_all[sl], wb_all[sl], k=k, path="gemv", threshold=args.threshold)
+                torch.cuda.synchronize()
+                out["shadow"] = {"uncertified_queries_in_the_last_batch": idx.get_option("last_uncertified"),
+                                 "uncertified_queries_total": idx.get_option("total_uncertified"),
+                                 "queries_total": idx.get_option("total_shadow_queries"),
+                                 "same_batch_on_the_exact_fp32_scan_ms": (time.perf_counter() - t0) / 2 * 1e3,
+                                 "what": "fp32 rows + bf16 shadows; tensor-core preselection of k + k/2 + 32 rows per query, exact fp32 "
+                                         "re-score, per-query exactness certificate, uncertified queries re-run on the exact scan"}
             if with_cpu:
                 out["cpu_baseline"] = cpu_baseline(n_rows, dtype, k)
         if with_dropin and world == 1 and nq == 1:
@@ -675,8 +694,8 @@ def main():
         r = measure(name, max(3, min(args.reps, 7)), with_cpu=False, with_dropin=False)
         if rank == 0:
             secondary.append({k: r[k] for k in ("config", "dtype", "value", "unit", "ms_per_step", "queries_per_s", "repetitions",
-                                                "e2e", "roofline", "clocks", "parity_check", "gpu_launches", "hbm_gbs_all_gpus")
-                              if k in r} | ({"exchange_breakdown": r["exchange_breakdown"]} if "exchange_breakdown" in r else {}))
+                                                "e2e", "roofline", "clocks", "parity_check", "gpu_launches", "hbm_gbs_all_gpus",
+                                                "exchange_breakdown", "shadow") if k in r})
     if rank == 0:
         sampler.stop()
         line["secondary"] = secondary
