@@ -69,8 +69,11 @@ def _embedding_row(e) -> np.ndarray:
 class _DeviceLibrary:
     """Keeps a SegmentIndex in step with an append-only `audio_segments` list (:797)."""
 
-    def __init__(self, dtype: str = "fp32", device: int = 0):
+    def __init__(self, dtype: str = "fp32", device: int = 0, tensor_core_batches: bool = False):
         self.dtype, self.device = dtype, device
+        # fp32 library: keep bf16 shadows so that batches (search_many, SearchBatcher, search_batch)
+        # are preselected on the tensor cores and re-scored exactly (SegmentIndex.enable_tensor_core_batches)
+        self.tensor_core_batches = tensor_core_batches and dtype == "fp32"
         self.index: SegmentIndex | None = None
         self.n_synced = 0
         self._last_seg = None
@@ -81,7 +84,7 @@ class _DeviceLibrary:
         forgets them; rows loaded from a file are in the index already (load_library)."""
         fresh = table is not self._last_seg or table.generation != self._table_generation
         if self.index is None:
-            self.index = SegmentIndex(self.dtype, capacity=max(1024, len(table)), device=self.device)
+            self.index = self._new_index(len(table))
         elif fresh:
             self.index.clear()
         if fresh:
@@ -99,6 +102,12 @@ class _DeviceLibrary:
         self.n_synced = len(table)
         return self.index
 
+    def _new_index(self, n: int) -> SegmentIndex:
+        index = SegmentIndex(self.dtype, capacity=max(1024, n), device=self.device)
+        if self.tensor_core_batches:
+            index.enable_tensor_core_batches()
+        return index
+
     def adopt(self, index: SegmentIndex, table: SegmentTable) -> None:
         """Take a loaded (index, table) pair as the synced state."""
         if len(index) != len(table):
@@ -106,6 +115,8 @@ class _DeviceLibrary:
         if self.index is not None:
             self.index.close()
         self.index, self.dtype = index, index.dtype
+        if self.tensor_core_batches and index.dtype == "fp32":
+            index.enable_tensor_core_batches()
         self._last_seg, self._table_generation = table, table.generation
         table.bind_index(index)
         self.n_synced = len(table)
@@ -114,7 +125,7 @@ class _DeviceLibrary:
         if isinstance(segments, SegmentTable):
             return self._sync_table(segments)
         if self.index is None:
-            self.index = SegmentIndex(self.dtype, capacity=max(1024, len(segments)), device=self.device)
+            self.index = self._new_index(len(segments))
         # the reference only ever appends; if the list was replaced or shrunk, rebuild
         if self.n_synced > len(segments) or (self.n_synced and segments[self.n_synced - 1] is not self._last_seg):
             self.index.clear()
@@ -213,14 +224,17 @@ def _b200_search_many(self, queries: List[str]) -> List[Tuple[List[Dict], Dict]]
     return out
 
 
-def accelerate(search_system, dtype: str = "fp32", device: int = 0, columnar: bool = False):
+def accelerate(search_system, dtype: str = "fp32", device: int = 0, columnar: bool = False,
+               tensor_core_batches: bool = False):
     """Replace `search_system.search_with_fusion` (a reference DualPipelineAudioSearch, or any
     object with the same attributes) by the B200 path.  Returns the same object.
 
     `columnar=True` also replaces the `audio_segments` list by a SegmentTable holding the same
     records (the app's `audio_segments.extend(segments)`, :797, keeps working): embeddings then
-    live only in HBM and the library can be saved with `save_library`."""
-    search_system._cab_library = _DeviceLibrary(dtype, device)
+    live only in HBM and the library can be saved with `save_library`.
+    `tensor_core_batches=True` (fp32): batched calls (`search_many`, `enable_batching`,
+    `search_batch`) are preselected on the tensor cores from bf16 shadow rows and re-scored exactly."""
+    search_system._cab_library = _DeviceLibrary(dtype, device, tensor_core_batches)
     if columnar and not isinstance(search_system.audio_segments, SegmentTable):
         search_system.audio_segments = SegmentTable.from_segments(search_system.audio_segments)
     search_system.search_with_fusion = types.MethodType(_b200_search_with_fusion, search_system)
@@ -256,11 +270,11 @@ class DualPipelineAudioSearch:
     ingest are the reference's business: populate `audio_segments` with its segment records
     (:275-294) and set `text_embedder` to anything with `.encode(str) -> float32[384]`."""
 
-    def __init__(self, dtype: str = "fp32", device: int = 0, text_embedder=None):
+    def __init__(self, dtype: str = "fp32", device: int = 0, text_embedder=None, tensor_core_batches: bool = False):
         self.text_embedder = text_embedder
         self.stats = {"search_pipeline": PipelineStats("Search Pipeline", "Cosine Similarity")}   # :107
         self.audio_segments: List[Dict] = []                                                      # :115
-        self._cab_library = _DeviceLibrary(dtype, device)
+        self._cab_library = _DeviceLibrary(dtype, device, tensor_core_batches)
 
     def _analyze_query_for_weights(self, query: str):
         return query_weights.analyze_query_for_weights(query)

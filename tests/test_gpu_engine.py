@@ -191,3 +191,20 @@ def test_search_many_and_session_batching(search_cases):
     results, info = eng.search_with_fusion(texts[0])
     assert len(eng._cab_library.index) == len(f) + 5 and info["query"] == texts[0]
     batcher.close()
+
+
+def test_fp32_engine_with_tensor_core_batches(search_cases):
+    """`tensor_core_batches=True`: the fp32 drop-in keeps bf16 shadows; `search_many` with >= 64 query
+    strings is preselected on the tensor cores and still returns exactly the reference-golden dicts."""
+    case = search_cases[1]
+    a, b, f, _ = synth.library(case["seed"], case["n_rows"], case["n_queries"], case["plants"], case["partial"])
+    q = synth.raw_queries(case["seed"], 0, case["n_queries"])
+    embedder = FakeEmbedder({r["text"]: q[r["qi"]] for r in case["queries"]})
+    eng = DualPipelineAudioSearch(text_embedder=embedder, tensor_core_batches=True)
+    eng.audio_segments.extend(segments_from_arrays(a, b, f))
+    texts = [r["text"] for r in case["queries"]]
+    many = eng.search_many([texts[i % len(texts)] for i in range(80)])
+    index = eng._cab_library.index
+    assert index.get_option("tensor_core_shadow") == 1 and index.get_option("total_shadow_queries") == 80
+    for i, (results, info) in enumerate(many):
+        _check(results, info, case["queries"][i % len(texts)])
