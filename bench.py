@@ -22,8 +22,10 @@ What the one JSON line (rank 0) carries:
                         (every returned row + every planted neighbour regenerated on the host);
                         N > 1: also the sharded answer against ONE index holding all rows
   secondary             the other BASELINE configs measured in the same process
-                        (N = 1: 10M fp32 single query, 10M bf16 x 256 queries on tensor cores,
-                        the pruning worst cases; N > 1: 12.5M bf16 per GPU = 100M over 8)
+                        (N = 1: 10M bf16 x 256 queries on tensor cores, the same batch on an fp32
+                        library through bf16 shadows + exact re-score, 10M fp32 single query;
+                        N > 1: 12.5M bf16 per GPU = 100M over 8; --secondary selects others,
+                        e.g. the pruning worst cases)
   cpu_baseline          the oracle port on the host cores (N = 1)
 
 `value` is queries/s normalised to 1M-segment libraries, i.e. queries/s x (global segments / 1M):
@@ -64,7 +66,7 @@ WORKLOADS = {
     "10m_bf16_q256_top100_clustered": (10_000_000, "bf16", 256, 100, "gemm", "clustered"),
 }
 # the tensor-core batch first: it is the power-cap-sensitive one (the HBM-bound scans barely notice the SM clock)
-SECONDARY = {1: ["10m_bf16_q256_top100", "10m_fp32_q1_top10"], "multi": ["12m5_bf16_q1_top100"]}
+SECONDARY = {1: ["10m_bf16_q256_top100", "10m_fp32_q256_top10_tc", "10m_fp32_q1_top10"], "multi": ["12m5_bf16_q1_top100"]}
 W_CLASSES = [0.5, 0.2, 0.3, 0.4, 0.6, 0.7, 0.8]       # the achievable w_asr classes (audio_search.py:593-620)
 
 
