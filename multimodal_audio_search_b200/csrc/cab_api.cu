@@ -958,7 +958,9 @@ static int finish_outputs(cab_index *idx, int nq, int k, const UserOut &o, cudaS
 
 // Shadow path (fp32 library, tensor-core preselection): read the per-query certificates of the batch
 // that just ran and re-run every query that is not provably exact on the exact scan, into the same
-// output slots.  Few of them: one by one; more than a quarter of the batch: the whole batch.
+// output slots.  Most of the batch uncertified: the whole batch goes to the exact scan.  Otherwise
+// the uncertified queries are gathered into one contiguous batch (register-tiled exact scan, 4
+// queries per corpus pass), their results come back through host memory and are scattered.
 static int rerun_uncertified(cab_index *idx, const float *queries, int queries_loc, const double *w_asr,
                              const double *w_audio, int k, double threshold, const UserOut &o, cudaStream_t s) {
     const int nq = idx->cert_pending;
@@ -966,24 +968,55 @@ static int rerun_uncertified(cab_index *idx, const float *queries, int queries_l
     std::vector<uint8_t> cert(size_t(nq), 1);
     CU(idx, cudaMemcpyAsync(cert.data(), idx->d_cert, size_t(nq), cudaMemcpyDeviceToHost, s));
     CU(idx, cudaStreamSynchronize(s));
-    int bad = 0;
-    for (uint8_t c : cert) bad += c == 0;
+    std::vector<int> todo;
+    for (int i = 0; i < nq; ++i) if (!cert[size_t(i)]) todo.push_back(i);
+    const int bad = int(todo.size());
     idx->last_uncertified = bad; idx->total_uncertified += bad; idx->total_shadow_queries += nq;
     if (bad == 0) return CAB_OK;
     int rc;
-    if (bad * 4 > nq) {
+    if (bad * 4 > nq * 3) {
         if ((rc = run_local(idx, queries, queries_loc, w_asr, w_audio, nq, k, threshold, CAB_PATH_GEMV, &o, nullptr, nullptr, s))) return rc;
         return finish_outputs(idx, nq, k, o, s);
     }
-    for (int i = 0; i < nq; ++i) {
-        if (cert[size_t(i)]) continue;
-        const size_t off = size_t(i) * k;
-        const UserOut oi{o.index ? o.index + off : nullptr, o.fusion ? o.fusion + off : nullptr, o.asr ? o.asr + off : nullptr,
-                         o.audio ? o.audio + off : nullptr, o.flags ? o.flags + off : nullptr, o.count ? o.count + i : nullptr, o.loc};
-        if ((rc = run_local(idx, queries + size_t(i) * CAB_DIM, queries_loc, w_asr + i, w_audio + i, 1, k, threshold, CAB_PATH_GEMV,
-                            &oi, nullptr, nullptr, s))) return rc;
-        if ((rc = finish_outputs(idx, 1, k, oi, s))) return rc;
+    // gather the queries (device buffer) and their weights
+    const size_t qbytes = size_t(CAB_DIM) * sizeof(float);
+    float *d_q = nullptr;
+    CU(idx, cudaMalloc((void **)&d_q, size_t(bad) * qbytes));
+    const size_t nb = size_t(bad);
+    std::vector<double> wa(nb), wb(nb);
+    cudaError_t e = cudaSuccess;
+    for (int j = 0; j < bad && e == cudaSuccess; ++j) {
+        wa[size_t(j)] = w_asr[todo[size_t(j)]]; wb[size_t(j)] = w_audio[todo[size_t(j)]];
+        e = cudaMemcpyAsync(d_q + size_t(j) * CAB_DIM, queries + size_t(todo[size_t(j)]) * CAB_DIM, qbytes,
+                            queries_loc == CAB_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s);
     }
+    if (e != cudaSuccess) { cudaFree(d_q); return fail(idx, CAB_ERR_CUDA, "gathering uncertified queries: %s", cudaGetErrorString(e)); }
+    const size_t n = size_t(bad) * k;
+    std::vector<int64_t> t_index(n); std::vector<double> t_fusion(n); std::vector<float> t_asr(n), t_audio(n);
+    std::vector<uint8_t> t_flags(n); std::vector<int32_t> t_count(nb);
+    const UserOut tmp{t_index.data(), t_fusion.data(), t_asr.data(), t_audio.data(), t_flags.data(), t_count.data(), CAB_HOST};
+    rc = run_local(idx, d_q, CAB_DEVICE, wa.data(), wb.data(), bad, k, threshold, CAB_PATH_GEMV, &tmp, nullptr, nullptr, s);
+    if (rc == CAB_OK) rc = finish_outputs(idx, bad, k, tmp, s);
+    cudaFree(d_q);                                       // synchronises; the scan has finished (host outputs)
+    if (rc != CAB_OK) return rc;
+    const bool dev = o.loc == CAB_DEVICE;
+    auto put = [&](void *dst_base, const void *src_base, size_t elem, size_t count, int j) -> cudaError_t {
+        if (!dst_base) return cudaSuccess;
+        uint8_t *dst = static_cast<uint8_t *>(dst_base) + size_t(todo[size_t(j)]) * count * elem;
+        const uint8_t *src = static_cast<const uint8_t *>(src_base) + size_t(j) * count * elem;
+        if (!dev) { memcpy(dst, src, count * elem); return cudaSuccess; }
+        return cudaMemcpyAsync(dst, src, count * elem, cudaMemcpyHostToDevice, s);
+    };
+    for (int j = 0; j < bad && e == cudaSuccess; ++j) {
+        e = put(o.index, t_index.data(), 8, size_t(k), j);
+        if (e == cudaSuccess) e = put(o.fusion, t_fusion.data(), 8, size_t(k), j);
+        if (e == cudaSuccess) e = put(o.asr, t_asr.data(), 4, size_t(k), j);
+        if (e == cudaSuccess) e = put(o.audio, t_audio.data(), 4, size_t(k), j);
+        if (e == cudaSuccess) e = put(o.flags, t_flags.data(), 1, size_t(k), j);
+        if (e == cudaSuccess) e = put(o.count, t_count.data(), 4, 1, j);
+    }
+    if (e == cudaSuccess && dev) e = cudaStreamSynchronize(s);       // the temporaries die with this frame
+    if (e != cudaSuccess) return fail(idx, CAB_ERR_CUDA, "scattering re-run results: %s", cudaGetErrorString(e));
     return CAB_OK;
 }
 

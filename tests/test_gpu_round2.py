@@ -414,6 +414,21 @@ def test_fp32_batches_on_tensor_cores_with_exactness_certificates():
     exact_low = idx.search(q, wa, wb, k=40, threshold=0.12, path="gemv")
     same(low, exact_low, "k=40")
     assert idx.get_option("total_shadow_queries") >= 5 * nq
+    # a batch in which only SOME queries fail their certificate (gathered re-run): 70 queries with 128
+    # strong planted rows each (certified at k = 100), 26 queries whose whole top-100 is dense noise
+    mix = SegmentIndex("fp32", capacity=n)
+    mix.append_synth(seed + 1, n, 0, n, n_queries=70, plants=128)
+    mix.enable_tensor_core_batches()
+    qm = synth.raw_queries(seed + 1, 0, nq)
+    exact_mix = mix.search(qm, wa, wb, k=100, path="gemv")
+    for variant in (qm, torch.from_numpy(qm).cuda()):
+        got_mix = mix.search(variant, wa, wb, k=100)
+        bad = mix.get_option("last_uncertified")
+        assert 0 < bad <= 0.75 * nq, bad
+        same(got_mix, exact_mix, "mixed batch")
+        gc = got_mix.count.cpu().numpy() if hasattr(got_mix.count, "cpu") else got_mix.count
+        np.testing.assert_array_equal(gc, exact_mix.count)
+    mix.close()
     with pytest.raises(Exception, match="fp32"):
         SegmentIndex("bf16").set_option("tensor_core_shadow", 1)
     idx.enable_tensor_core_batches(False)
