@@ -168,6 +168,7 @@ class SegmentTable(Sequence):
         self._pending: List[tuple] = []
         self._pending_row0 = 0
         self._index = None                                       # SegmentIndex for embedding fetches
+        self._fast = None                                        # memoryviews of the loaded columns (record())
         self.generation = 0                                      # bumped by clear()
 
     # ---- construction ------------------------------------------------------------------------
@@ -316,7 +317,47 @@ class SegmentTable(Sequence):
     def success_flags(self, i: int):
         return bool(self._num_at("asr_success", i)), bool(self._num_at("audio_success", i))
 
+    def _fast_views(self):
+        """memoryviews of the loaded (base) columns: a scalar read through a memoryview returns a
+        Python int / float in ~40 ns, through numpy (memmap) indexing in ~150 ns + a conversion; a
+        result record reads 6 numbers and 10 text offsets."""
+        num = {name: memoryview(np.ascontiguousarray(self._num[name])) for name, _ in NUMERIC_COLUMNS}
+        text = {}
+        for name in TEXT_COLUMNS:
+            col = self._text[name]
+            text[name] = (memoryview(np.ascontiguousarray(col.offsets, dtype=np.int64)), col.blob)
+        self._fast = (num, text)
+        return self._fast
+
+    def _base_record(self, i: int) -> SegmentRecord:
+        num, text = self._fast or self._fast_views()
+
+        def txt(name):
+            offs, blob = text[name]
+            lo, hi = offs[i], offs[i + 1]
+            return bytes(blob[lo:hi]).decode("utf-8") if hi > lo else ""
+        fields = {
+            "segment_id": txt("segment_id") or f"seg_{i}",
+            "start_time": num["start_time"][i],
+            "end_time": num["end_time"][i],
+            "duration": num["duration"][i],
+            "asr_text": txt("asr_text"),
+            "asr_success": num["asr_success"][i] != 0,
+            "audio_description": txt("audio_description"),
+            "audio_success": num["audio_success"][i] != 0,
+            "sample_rate": num["sample_rate"][i],
+        }
+        file = txt("file")
+        if file:
+            fields["file"] = file
+        extra = txt("extra_json")
+        if extra:
+            fields.update(json.loads(extra))
+        return SegmentRecord(self, i, fields)
+
     def record(self, i: int) -> SegmentRecord:
+        if i < self._n_base:
+            return self._base_record(i)
         fields = {
             "segment_id": self._text["segment_id"][i] or f"seg_{i}",
             "start_time": float(self._num_at("start_time", i)),
