@@ -13,7 +13,7 @@ timeout 600 $B2 > gpurun_out/plain2.log 2>&1; echo "gemm rc=$?"
 timeout 600 $B3 > gpurun_out/plain3.log 2>&1; echo "10m rc=$?"
 echo "== launch lists"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $B1 > gpurun_out/ncu1.log 2>&1; echo "rc=$?"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_gemm.csv $B2 > gpurun_out/ncu3.log 2>&1; echo "rc=$?"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 613 -c 80 --csv --log-file gpurun_out/launches_gemm.csv $B2 > gpurun_out/ncu3.log 2>&1; echo "rc=$?"
 echo "== full captures"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:cab_scan -s 6 -c 1 -o gpurun_out/prof_gemv -f $B1 > gpurun_out/ncu2.log 2>&1; echo "rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_scan -s 3 -c 1 -o gpurun_out/prof_gemm -f $B2 > gpurun_out/ncu4.log 2>&1; echo "rc=$?"
