@@ -908,9 +908,9 @@ static int run_local(cab_index *idx, const float *queries, int queries_loc, cons
             eb.out_asr = ea.out_asr + size_t(q0) * k; eb.out_audio = ea.out_audio + size_t(q0) * k;
             eb.out_flags = ea.out_flags + size_t(q0) * k; eb.out_count = ea.out_count + q0;
             if (q0 + batch < nq) eb.done_epoch = 0;                                   // only the last batch signals completion
-            launch_finalize(fa, &eb, s);
+            launch_finalize(fa, &eb, idx->sm_count, s);
         } else {
-            launch_finalize(fa, nullptr, s);
+            launch_finalize(fa, nullptr, idx->sm_count, s);
         }
         idx->launches += use_gemm ? 3 : 2;          // (prologue +) scan + finalize
     }

@@ -18,8 +18,10 @@
 
 namespace cab {
 
-constexpr int kFinThreads = 1024;
-constexpr int kFinWarps = kFinThreads / 32;
+// One CTA per query.  1024 threads (one CTA per SM) when the queries fit one wave: the shortest
+// latency for a single search.  512 threads (two CTAs per SM) for bigger batches: 256 queries run as
+// one wave instead of two, and their latency-bound phases overlap on each SM.
+constexpr int kFinThreadsMax = 1024;
 constexpr int kSortCap = 4096;          // keys in the shared-memory selection buffer
 constexpr int kFinUnroll = 2;           // slots loaded per thread per round
 constexpr int kMaxHeads = 1024;         // scan CTAs (partial lists) the fast path can rank
@@ -258,9 +260,10 @@ __device__ __forceinline__ void emit_ranked(CandAt cand_at, int n_cand, int qi, 
 }
 
 // ---- finalize ---------------------------------------------------------------------------------
-template <int DT>
-__global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, EmitArgs e) {
+template <int DT, int kFinThreads>
+__global__ void __launch_bounds__(kFinThreads, kFinThreadsMax / kFinThreads) finalize_kernel(FinalizeArgs a, EmitArgs e) {
     using TR = RowTraits<DT>;
+    constexpr int kFinWarps = kFinThreads / 32;
     __shared__ uint64_t s_sort[kSortCap];
     __shared__ cab_candidate s_cand[kMaxK];
     __shared__ uint64_t s_head[kMaxHeads];
@@ -568,19 +571,27 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, E
     host_signal(e);
 }
 
-void launch_finalize(const FinalizeArgs &a, const EmitArgs *fused_emit, cudaStream_t s) {
+void launch_finalize(const FinalizeArgs &a, const EmitArgs *fused_emit, int sm_count, cudaStream_t s) {
     EmitArgs e{};
     if (fused_emit) e = *fused_emit;
     // Programmatic dependent launch: the finalize grid is staged while the scan still runs and
     // starts the moment it completes (the kernel begins with griddepcontrol.wait).
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(a.n_queries); cfg.blockDim = dim3(kFinThreads); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    // a sharded search whose merge rides in this kernel spins on the peers' flags: keep its CTAs at
+    // one per SM (all co-resident, no second CTA starved behind a spinning one)
+    const bool wide = a.n_queries <= sm_count || (a.peer.world && e.out_index);
+    cfg.gridDim = dim3(a.n_queries); cfg.blockDim = dim3(wide ? kFinThreadsMax : kFinThreadsMax / 2); cfg.dynamicSmemBytes = 0; cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    if (a.dtype == CAB_BF16) cudaLaunchKernelEx(&cfg, finalize_kernel<CAB_BF16>, a, e);
-    else cudaLaunchKernelEx(&cfg, finalize_kernel<CAB_F32>, a, e);
+    if (a.dtype == CAB_BF16) {
+        if (wide) cudaLaunchKernelEx(&cfg, finalize_kernel<CAB_BF16, kFinThreadsMax>, a, e);
+        else cudaLaunchKernelEx(&cfg, finalize_kernel<CAB_BF16, kFinThreadsMax / 2>, a, e);
+    } else {
+        if (wide) cudaLaunchKernelEx(&cfg, finalize_kernel<CAB_F32, kFinThreadsMax>, a, e);
+        else cudaLaunchKernelEx(&cfg, finalize_kernel<CAB_F32, kFinThreadsMax / 2>, a, e);
+    }
 }
 
 // ---- emit as its own launch: merge of several candidate lists (cab_merge_candidates, and sharded

@@ -184,7 +184,7 @@ struct FinalizeArgs {
 };
 struct EmitArgs;
 // fused_emit != nullptr (single candidate list): the emit stage runs inside the same kernel.
-void launch_finalize(const FinalizeArgs &a, const EmitArgs *fused_emit, cudaStream_t s);
+void launch_finalize(const FinalizeArgs &a, const EmitArgs *fused_emit, int sm_count, cudaStream_t s);
 
 struct EmitArgs {
     const cab_candidate *cands;   // [n_lists][n_queries][k]
