@@ -250,14 +250,15 @@ def _peer_worker(rank, world, port, seed, n, nq, out_path):
     dist.destroy_process_group()
 
 
-def test_peer_exchange_two_processes_one_gpu(tmp_path):
-    """World of 2 ranks = 2 processes, both on cuda:0, exchange buffers shared through CUDA IPC: the
+@pytest.mark.parametrize("world", [2, 3])
+def test_peer_exchange_two_processes_one_gpu(tmp_path, world):
+    """World of 2 (3) ranks = 2 (3) processes, all on cuda:0, exchange buffers shared through CUDA IPC: the
     finalize kernel's peer stores + epoch flags + merge must give every rank exactly the answer of
     one index over the whole library.  (The GPU time-slices the two contexts; the flag waits are
     bounded, so a protocol bug fails the test instead of hanging the box.)"""
     torch = pytest.importorskip("torch")
     import torch.multiprocessing as mp
-    seed, n, nq, world = 41, 90_000, 100, 2
+    seed, n, nq = 41, 90_000, 100                    # world = 3, k = 100: 300 candidates per query -> the merge SORTS
     whole = SegmentIndex("fp32", capacity=n)
     whole.append_synth(seed, n, 0, n, n_queries=nq, plants=60, partial=True)
     q = synth.raw_queries(seed, 0, nq)
@@ -266,7 +267,7 @@ def test_peer_exchange_two_processes_one_gpu(tmp_path):
     want = [whole.search(q[a:b], wa[a:b], wb[a:b], k=k) for a, b, k in cases]
     whole.close()
     out = str(tmp_path / "peer")
-    port = 29500 + (os.getpid() % 2000)
+    port = 29500 + (os.getpid() % 2000) + 7 * world
     ctx = mp.spawn(_peer_worker, args=(world, port, seed, n, nq, out), nprocs=world, join=False)
     deadline = 240
     import time
