@@ -55,7 +55,9 @@ typedef enum cab_status {
 typedef enum cab_dtype { CAB_F32 = 0, CAB_BF16 = 1 } cab_dtype;      /* storage type of rows */
 typedef enum cab_loc { CAB_HOST = 0, CAB_DEVICE = 1 } cab_loc;
 typedef enum cab_path {                                              /* which scan kernel */
-    CAB_PATH_AUTO = 0,       /* GEMV for few queries, tensor-core GEMM for >= 64 (bf16 only) */
+    CAB_PATH_AUTO = 0,       /* GEMV for few queries; tensor-core GEMM from option "gemm_min_queries" on
+                                (default: 4 queries on libraries of >= 65 536 segments, else 64) for a bf16
+                                index or an fp32 index with bf16 shadows */
     CAB_PATH_GEMV = 1,       /* HBM-bound fused GEMV + top-k (CUDA cores, fp32 accumulate) */
     CAB_PATH_GEMM = 2        /* tcgen05/TMEM GEMM with fused weighting/top-k epilogue (bf16) */
 } cab_path;

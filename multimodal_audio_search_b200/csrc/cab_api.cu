@@ -71,7 +71,7 @@ struct cab_index {
     bool ev_in_pending = false, timed = false;
     // options
     GemvConfig gemv{0, 0, 0, 0};
-    int64_t opt_time_kernels = 0, opt_sync = 0, opt_gemm_min_queries = 64, opt_gemv_batch = 32;
+    int64_t opt_time_kernels = 0, opt_sync = 0, opt_gemm_min_queries = 0 /* auto, see gemm_min_queries() */, opt_gemv_batch = 32;
     int64_t opt_queries_settled = 0, opt_stamp_exchange = 0, opt_raw_dot = 0;
     int64_t opt_finalize_general = 0, opt_chunk_rows = 0;    // 0 = auto: 96 KB of corpus per chunk (fp32 32 rows, bf16 64), profiles/r01_gemv_chunk_sweep.md
     // peer-memory exchange (sharded search)
@@ -753,6 +753,15 @@ static int stage_params(cab_index *idx, const float *queries, int queries_loc, c
     return CAB_OK;
 }
 
+// Smallest batch that PATH_AUTO sends to the tensor cores.  Measured crossover (tools/crossover_probe.py,
+// profiles/r02_crossover.md): the tensor-core scan costs about the same for 2 as for 256 queries and
+// beats the register-tiled GEMV (4 queries per corpus pass) from 4 queries on, at every library size
+// from 100 K segments; below ~64 K segments its fixed cost (cluster launch, TMEM, tensor maps) loses.
+static int64_t gemm_min_queries(const cab_index *idx) {
+    if (idx->opt_gemm_min_queries > 0) return idx->opt_gemm_min_queries;
+    return idx->size >= 65536 ? 4 : 64;
+}
+
 // Stage parameters; run scan + finalize -> idx->d_cands[nq x k]; with `out` != null (single GPU)
 // the finalize kernel also emits the final results.
 struct UserOut {
@@ -797,7 +806,7 @@ static int run_local(cab_index *idx, const float *queries, int queries_loc, cons
         if (!gemm_path_available()) return fail(idx, CAB_ERR_INVALID, "tensor-core path not built");
         use_gemm = true;
     } else if (path == CAB_PATH_AUTO) {
-        use_gemm = (idx->dtype == CAB_BF16 || shadow_ok) && nq >= idx->opt_gemm_min_queries && gemm_path_available() && !idx->opt_raw_dot;
+        use_gemm = (idx->dtype == CAB_BF16 || shadow_ok) && nq >= gemm_min_queries(idx) && gemm_path_available() && !idx->opt_raw_dot;
     }
     const bool certified = use_gemm && idx->dtype == CAB_F32;
     const int k_sel = certified ? k_sel_shadow : k;                // rows selected by the scan per query
@@ -1310,7 +1319,7 @@ int cab_index_set_option(cab_index *idx, const char *key, int64_t value) {
     }
     else if (k == "stamp_exchange") { idx->opt_stamp_exchange = value != 0; idx->stamp_calls = 0; }
     else if (k == "gemv_chunk_rows") { if (value < 0 || value > 4096) return fail(idx, CAB_ERR_INVALID, "gemv_chunk_rows in 0..4096 (0 = auto)"); idx->opt_chunk_rows = value; }
-    else if (k == "gemm_min_queries") { if (value < 1) return fail(idx, CAB_ERR_INVALID, "gemm_min_queries >= 1"); idx->opt_gemm_min_queries = value; }
+    else if (k == "gemm_min_queries") { if (value < 0) return fail(idx, CAB_ERR_INVALID, "gemm_min_queries >= 0 (0 = auto)"); idx->opt_gemm_min_queries = value; }
     else if (k == "gemv_batch") { if (value < 1 || value > 64) return fail(idx, CAB_ERR_INVALID, "gemv_batch in 1..64"); idx->opt_gemv_batch = value; }
     else return fail(idx, CAB_ERR_INVALID, "unknown option '%s'", key);
     return CAB_OK;
@@ -1333,7 +1342,7 @@ int64_t cab_index_get_option(const cab_index *idx, const char *key) {
     if (k == "total_shadow_queries") return idx->total_shadow_queries;
     if (k == "stamp_exchange") return idx->opt_stamp_exchange;
     if (k == "gemv_chunk_rows") return idx->opt_chunk_rows;
-    if (k == "gemm_min_queries") return idx->opt_gemm_min_queries;
+    if (k == "gemm_min_queries") return gemm_min_queries(idx);
     if (k == "gemv_batch") return idx->opt_gemv_batch;
     if (k == "sm_count") return idx->sm_count;
     if (k == "gemv_query_tile") return idx->gemv.query_tile;
