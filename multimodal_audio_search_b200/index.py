@@ -137,7 +137,7 @@ class SegmentIndex:
 
     def enable_tensor_core_batches(self, on: bool = True):
         """fp32 index only: keep bf16 shadow copies of both corpora (+50 % HBM) so that batches of
-        >= 64 queries are PRE-selected on the tensor cores, re-scored exactly from the fp32 rows and
+        >= 4 queries (libraries of >= 64 K segments) are PRE-selected on the tensor cores, re-scored exactly from the fp32 rows and
         certified per query; a query whose top-k is not provably exact is re-run on the exact scan
         (`get_option("last_uncertified")` says how many of the last batch).  Results are those of
         the fp32 GEMV path; throughput is the bf16 tensor-core path's."""
