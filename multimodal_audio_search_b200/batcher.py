@@ -2,7 +2,7 @@
 
 The reference answers one query per `search_with_fusion` call (audio_search.py:624), one engine
 per browser session (:708-711).  When several sessions (threads) search the SAME library, their
-queries can share a corpus pass: 4 queries per pass in the GEMV scan, and from 64 queries on a bf16
+queries can share a corpus pass: 4 queries per pass in the GEMV scan, and from 4 queries on a bf16 (or shadowed fp32)
 index the tensor-core scan ("makes Q >= 64 batches arise naturally
 from concurrent sessions").  `SearchBatcher` collects the requests that arrive while the GPU is
 busy (or within `max_wait_s` of the first one) and issues ONE `SegmentIndex.search` for them.

@@ -202,7 +202,7 @@ def _b200_search_with_fusion(self, query: str) -> Tuple[List[Dict], Dict]:
 
 def _b200_search_many(self, queries: List[str]) -> List[Tuple[List[Dict], Dict]]:
     """`search_with_fusion` for several query strings with ONE scan batch (one corpus pass per 4
-    queries; the tensor-core scan from 64 queries on a bf16 library): the list of what
+    queries; the tensor-core scan from 4 queries on a bf16 or shadowed fp32 library): the list of what
     `search_with_fusion(q)` returns for each q, stats updated once per query."""
     if not self.audio_segments:
         return [([], {}) for _ in queries]
