@@ -1,7 +1,9 @@
 #!/usr/bin/env python3
 """Throughput of concurrent sessions through the SearchBatcher vs one query per call.
 
-    python tools/bench_batcher.py [segments] [dtype] [threads] [queries_per_thread]
+    python tools/bench_batcher.py [segments] [dtype] [threads] [queries_per_thread] [shadow]
+
+`shadow` (fp32 only): keep bf16 shadows so that batches are preselected on the tensor cores.
 """
 import json
 import os
@@ -21,7 +23,10 @@ def main():
     dtype = sys.argv[2] if len(sys.argv) > 2 else "fp32"
     n_threads = int(sys.argv[3]) if len(sys.argv) > 3 else 64
     per_thread = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+    shadow = len(sys.argv) > 5 and sys.argv[5] == "shadow" and dtype == "fp32"
     idx = SegmentIndex(dtype, capacity=n, device=0)
+    if shadow:
+        idx.enable_tensor_core_batches()
     idx.append_synth(11, n, 0, n, n_queries=64, plants=12, partial=False)
     q = synth.raw_queries(11, 0, 64)
     for i in range(5):
@@ -46,7 +51,7 @@ def main():
         dt = time.perf_counter() - t0
         st = batcher.stats
         batcher.close()
-        print(json.dumps({"segments": n, "dtype": dtype, "threads": n_threads, "queries": total,
+        print(json.dumps({"segments": n, "dtype": dtype + (" + bf16 shadows" if shadow else ""), "threads": n_threads, "queries": total,
                           "max_wait_s": max_wait, "serial_queries_per_s": round(serial_qps, 1),
                           "batched_queries_per_s": round(total / dt, 1), "speedup": round(total / dt / serial_qps, 2),
                           "gpu_calls": st.batches, "mean_batch": round(st.mean_batch, 1), "largest_batch": st.largest_batch}),
