@@ -561,7 +561,7 @@ def main():
                                  "uncertified_queries_total": idx.get_option("total_uncertified"),
                                  "queries_total": idx.get_option("total_shadow_queries"),
                                  "same_batch_on_the_exact_fp32_scan_ms": (time.perf_counter() - t0) / 2 * 1e3,
-                                 "what": "fp32 rows + bf16 shadows; tensor-core preselection of k + k/2 + 32 rows per query, exact fp32 "
+                                 "what": "fp32 rows + bf16 shadows; tensor-core preselection of max(96, k + k/2 + 32) rows per query, exact fp32 "
                                          "re-score, per-query exactness certificate, uncertified queries re-run on the exact scan"}
             if with_cpu:
                 out["cpu_baseline"] = cpu_baseline(n_rows, dtype, k)

@@ -243,7 +243,7 @@ CAB_API int cab_index_exchange_stamps(cab_index *idx, uint64_t *out, int max_row
  * "time_kernels", "sync_after_search", "stamp_exchange";
  * "tensor_core_shadow" = 1 (fp32 index): keep bf16 shadow copies of both corpora (+50 % memory);
  * cab_search batches of >= "gemm_min_queries" queries (default 4, k <= 112) are then PRE-selected on the
- * tensor cores from the shadows (k + k/2 + 32 rows per query), re-scored exactly from the fp32
+ * tensor cores from the shadows (max(96, k + k/2 + 32) rows per query), re-scored exactly from the fp32
  * rows, and certified per query: the top-k is provably the exact one when k re-scored candidates
  * lie above (scan score of the worst selected row + 4e-3, the bound on the bf16 error of a cosine
  * of unit vectors).  Uncertified queries are re-run on the exact GEMV scan before the call

@@ -794,7 +794,7 @@ static int run_local(cab_index *idx, const float *queries, int queries_loc, cons
     // shadows, the finalize kernel re-scores them exactly from the fp32 rows and certifies each query
     // (FinalizeArgs::cert_out); only a plain cab_search takes this route (the caller of run_local
     // re-runs uncertified queries on the exact scan).
-    const int k_sel_shadow = std::min(CAB_MAX_K, k + k / 2 + 32);
+    const int k_sel_shadow = std::min(CAB_MAX_K, std::max(96, k + k / 2 + 32));   // wide margin: re-scoring 96 rows costs microseconds, a failed certificate a corpus pass
     const bool shadow_ok = idx->dtype == CAB_F32 && idx->shadow_asr && out && !sh && !cand_dst && !idx->opt_raw_dot &&
                            k_sel_shadow >= k + 16 && idx->size > 0;
     bool use_gemm = false;
