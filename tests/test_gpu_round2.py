@@ -269,7 +269,7 @@ def test_peer_exchange_two_processes_one_gpu(tmp_path, world, dtype):
     want = [whole.search(q[a:b], wa[a:b], wb[a:b], k=k, path="gemv") for a, b, k in cases]
     whole.close()
     out = str(tmp_path / "peer")
-    port = 29500 + (os.getpid() % 2000) + 7 * world
+    port = 29500 + (os.getpid() % 2000) + 7 * world + (3 if dtype == "bf16" else 0)      # one rendezvous port per variant
     ctx = mp.spawn(_peer_worker, args=(world, port, seed, n, nq, out, dtype), nprocs=world, join=False)
     deadline = 240
     import time
