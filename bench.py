@@ -629,11 +629,28 @@ def main():
     def cross_check():
         per, nq, k = 60_000, 40, 10
         n_total = per * world
-        whole = SegmentIndex("fp32", capacity=n_total, device=local)
+        exact, within, n, detail = 0, 0, 0, []
+        for dtype in ("fp32", "bf16"):            # bf16 shards: batches of >= 4 queries take the tensor-core scan
+            e_, w_, n_ = cross_check_one(dtype, per, nq, n_total, detail)
+            exact, within, n = exact + e_, within + w_, n + n_
+        t = torch.tensor([n - exact, n - within], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        torch.cuda.synchronize()
+        dist.barrier()
+        return {"ok": int(t[1].item()) == 0, "queries": n, "not_bit_identical_over_all_ranks": int(t[0].item()),
+                "outside_tolerance_over_all_ranks": int(t[1].item()), "tolerance": 1e-5, "examples_rank0": detail,
+                "what": f"{world} x {per} segments, fp32 and bf16 (bf16 batches on the tensor cores): ShardedSearcher "
+                        f"({exchange_state['kind']}) on every rank vs one index over all rows on the same rank (exact scan); identical "
+                        f"indices and float64 fusion scores except swaps between rows closer than the fp32 tolerance at the k-th "
+                        f"boundary; fused and separate merge, device and host outputs"}
+
+    def cross_check_one(dtype, per, nq, n_total, detail):
+        whole = SegmentIndex(dtype, capacity=n_total, device=local)
         whole.append_synth(SEED + 1, n_total, 0, n_total, n_queries=nq, plants=30, partial=True)
-        part = SegmentIndex("fp32", capacity=per, device=local)
+        part = SegmentIndex(dtype, capacity=per, device=local)
         part.append_synth(SEED + 1, n_total, rank * per, (rank + 1) * per, n_queries=nq, plants=30, partial=True)
         part.row_base = rank * per
+        part.set_option("gemm_min_queries", 4)
         sh = ShardedSearcher(part, rank, world, exchange=exchange_state["kind"], max_queries=64, max_k=100)
         q = synth.raw_queries(SEED + 1, 0, nq)
         qd = torch.from_numpy(q).cuda()
@@ -643,12 +660,12 @@ def main():
         # BASELINE north_star) may swap at the k-th boundary -- a shard keeps its own top-k, so the
         # sharded search sees a superset of the single index's candidates there.
         tol = 1e-5
-        exact, within, n, detail = 0, 0, 0, []
+        exact, within, n = 0, 0, 0
         # single queries (merge fused into the finalize kernel, one CTA), small batches (fused, several CTAs
         # behind one per-rank flag), two scan passes (separate merge launch), k = 10 / 100
         cases = [(i, i + 1, 10) for i in range(8)] + [(8, 9, 100), (2, 9, 10), (0, 32, 100), (0, 40, 10), (9, 10, 10), (0, 40, 100)]
         for lo, hi, kk in cases:
-            want = whole.search(q[lo:hi], wa[lo:hi], wb[lo:hi], k=kk)
+            want = whole.search(q[lo:hi], wa[lo:hi], wb[lo:hi], k=kk, path="gemv")
             got = sh.search(qd[lo:hi], wa[lo:hi], wb[lo:hi], k=kk, to_host=False)
             goth = sh.search(q[lo:hi], wa[lo:hi], wb[lo:hi], k=kk, to_host=True)
             for variant, g in (("device", got), ("host", goth)):
@@ -669,18 +686,12 @@ def main():
                     within += int(ok)
                     if len(detail) < 3:
                         d = sorted(set(a) ^ set(b))
-                        detail.append({"case": [lo, hi, kk], "variant": variant, "query": lo + j, "ok_within_tolerance": bool(ok),
+                        detail.append({"dtype": dtype, "case": [lo, hi, kk], "variant": variant, "query": lo + j, "ok_within_tolerance": bool(ok),
                                        "rows_only_in_one": d[:4], "their_scores": [a.get(r, b.get(r)) for r in d[:4]], "kth": kth})
-        t = torch.tensor([n - exact, n - within], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
         torch.cuda.synchronize()
         dist.barrier()
         whole.close(); part.close()
-        return {"ok": int(t[1].item()) == 0, "queries": n, "not_bit_identical_over_all_ranks": int(t[0].item()),
-                "outside_tolerance_over_all_ranks": int(t[1].item()), "tolerance": tol, "examples_rank0": detail,
-                "what": f"{world} x {per} segments: ShardedSearcher ({exchange_state['kind']}) on every rank vs one index "
-                        f"over all rows on the same rank; identical indices and float64 fusion scores except swaps between rows "
-                        f"closer than the fp32 tolerance at the k-th boundary; fused and separate merge, device and host outputs"}
+        return exact, within, n
 
     line = measure(args.workload, args.reps, with_cpu=not args.no_cpu_baseline and world == 1, with_dropin=not args.no_dropin)
     if world > 1:
