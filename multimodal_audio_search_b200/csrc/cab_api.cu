@@ -762,6 +762,14 @@ static int64_t gemm_min_queries(const cab_index *idx) {
     return idx->size >= 65536 ? 4 : 64;
 }
 
+// fp32 library with bf16 shadows: rows preselected per query by the tensor-core scan (wide margin:
+// re-scoring 96 rows costs microseconds, a failed certificate a corpus pass), and whether the route
+// applies to this index / k at all.
+static int shadow_k_sel(int k) { return std::min(CAB_MAX_K, std::max(96, k + k / 2 + 32)); }
+static bool shadow_possible(const cab_index *idx, int k) {
+    return idx->dtype == CAB_F32 && idx->shadow_asr && !idx->opt_raw_dot && shadow_k_sel(k) >= k + 16 && idx->size > 0;
+}
+
 // Stage parameters; run scan + finalize -> idx->d_cands[nq x k]; with `out` != null (single GPU)
 // the finalize kernel also emits the final results.
 struct UserOut {
@@ -794,9 +802,8 @@ static int run_local(cab_index *idx, const float *queries, int queries_loc, cons
     // shadows, the finalize kernel re-scores them exactly from the fp32 rows and certifies each query
     // (FinalizeArgs::cert_out); only a plain cab_search takes this route (the caller of run_local
     // re-runs uncertified queries on the exact scan).
-    const int k_sel_shadow = std::min(CAB_MAX_K, std::max(96, k + k / 2 + 32));   // wide margin: re-scoring 96 rows costs microseconds, a failed certificate a corpus pass
-    const bool shadow_ok = idx->dtype == CAB_F32 && idx->shadow_asr && out && !sh && !cand_dst && !idx->opt_raw_dot &&
-                           k_sel_shadow >= k + 16 && idx->size > 0;
+    const int k_sel_shadow = shadow_k_sel(k);
+    const bool shadow_ok = shadow_possible(idx, k) && out && !sh && !cand_dst;
     bool use_gemm = false;
     if (path == CAB_PATH_GEMM) {
         if (idx->dtype != CAB_BF16 && !shadow_ok)
@@ -1233,8 +1240,30 @@ int cab_search_sharded(cab_index *idx, const float *queries, int queries_loc, co
     const UserOut o{out_index, out_fusion, out_asr, out_audio, out_flags, out_count, out_loc};
     int rc = enter_stream(idx, s);
     if (rc != CAB_OK) return rc;
-    rc = run_local(idx, queries, queries_loc, w_asr, w_audio, n_queries, k, threshold, path, &o, nullptr, &sh, s);
-    if (rc != CAB_OK) return rc;
+    if (path != CAB_PATH_GEMV && shadow_possible(idx, k) && n_queries >= gemm_min_queries(idx) && gemm_path_available()) {
+        // fp32 shard with bf16 shadows, a batch: the shard's EXACT top-k comes from the certified
+        // single-index route (tensor-core preselection, exact re-score, local re-runs of uncertified
+        // queries -- a purely local matter, no rank needs to agree), lands in device scratch, is packed
+        // into candidate records and pushed; the merge below is the ordinary one.
+        CU(idx, cudaSetDevice(idx->device));
+        if ((rc = ensure_dev(idx, &idx->d_out, &idx->d_out_bytes, out_layout(n_queries, CAB_MAX_K).total))) return rc;
+        const OutLayout L = out_layout(n_queries, k);
+        uint8_t *d = idx->d_out;
+        const UserOut lo{reinterpret_cast<int64_t *>(d + L.index), reinterpret_cast<double *>(d + L.fusion),
+                         reinterpret_cast<float *>(d + L.asr), reinterpret_cast<float *>(d + L.audio), d + L.flags,
+                         reinterpret_cast<int32_t *>(d + L.count), CAB_DEVICE};
+        if ((rc = run_local(idx, queries, queries_loc, w_asr, w_audio, n_queries, k, threshold, CAB_PATH_AUTO, &lo, nullptr, nullptr, s))) return rc;
+        if (idx->cert_pending && (rc = rerun_uncertified(idx, queries, queries_loc, w_asr, w_audio, k, threshold, lo, s))) return rc;
+        if ((rc = stage_params(idx, nullptr, CAB_DEVICE, w_asr, w_audio, n_queries, s, nullptr))) return rc;   // the merge's weights
+        pp.q0 = 0; pp.signal = 1;
+        launch_pack_push(lo.index, lo.asr, lo.audio, lo.flags, lo.count, n_queries, k, pp, s);
+        idx->launches += 1;
+        CU(idx, cudaGetLastError());
+        sh.fused = false;
+    } else {
+        rc = run_local(idx, queries, queries_loc, w_asr, w_audio, n_queries, k, threshold, path, &o, nullptr, &sh, s);
+        if (rc != CAB_OK) return rc;
+    }
     if (!sh.fused) {
         // many queries / several scan passes / an empty shard: the merge is its own launch
         EmitArgs ea{};

@@ -191,6 +191,35 @@ void launch_peer_push(const cab_candidate *local, int n_queries, int k, const Pe
     peer_push_kernel<<<1, 256, 0, s>>>(local, n_queries, k, peer);
 }
 
+// Sharded search of an fp32 library through its bf16 shadows: the shard's EXACT top-k was produced by
+// the certified single-index route as ordinary result arrays (device); turn query blockIdx.x's row
+// into candidate records and push them like a finalize kernel would.
+__global__ void __launch_bounds__(128) pack_push_kernel(const int64_t *__restrict__ index, const float *__restrict__ asr,
+                                                        const float *__restrict__ audio, const uint8_t *__restrict__ flags,
+                                                        const int32_t *__restrict__ count, int k, PeerPush p) {
+    __shared__ cab_candidate s_cand[kMaxK];
+    __shared__ int s_last;
+    const int qi = blockIdx.x;
+    const int c = count[qi];                                  // -1: the query holds NaN/Inf
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        const bool have = i < c;
+        const size_t o = size_t(qi) * k + i;
+        cab_candidate cd;
+        cd.index = have ? index[o] : (c < 0 ? kBadQueryIndex : int64_t(-1));
+        cd.asr_sim = have ? asr[o] : 0.f;
+        cd.audio_sim = have ? audio[o] : 0.f;
+        cd.flags = have ? uint32_t(flags[o]) : 0u;
+        cd.pad = 0u;
+        s_cand[i] = cd;
+    }
+    __syncthreads();
+    peer_push_and_signal(p, s_cand, p.q0 + qi, k, &s_last);
+}
+void launch_pack_push(const int64_t *index, const float *asr, const float *audio, const uint8_t *flags, const int32_t *count,
+                      int n_queries, int k, const PeerPush &peer, cudaStream_t s) {
+    pack_push_kernel<<<n_queries, 128, 0, s>>>(index, asr, audio, flags, count, k, peer);
+}
+
 // ---- emit: rank one query's candidates and write the first k ------------------------------------------
 // `cand_at(t)` returns candidate t of n_cand (<= blockDim.x, <= kEmitMax).  score/index/pos are
 // shared arrays of kEmitMax entries.  Order: (float64 fusion desc, global index asc) = Python's

@@ -226,5 +226,9 @@ constexpr int64_t kBadQueryIndex = -2;
 // was nothing to scan; otherwise the finalize kernel pushes).
 void launch_peer_push(const cab_candidate *local, int n_queries, int k, const PeerPush &peer, cudaStream_t s);
 void launch_emit(const EmitArgs &a, cudaStream_t s);
+// Result arrays [n_queries x k] (device) of this shard -> candidate records, pushed to every rank;
+// raises this rank's flags (peer.signal must be 1, peer.q0 the first query).
+void launch_pack_push(const int64_t *index, const float *asr, const float *audio, const uint8_t *flags, const int32_t *count,
+                      int n_queries, int k, const PeerPush &peer, cudaStream_t s);
 
 }  // namespace cab

@@ -213,10 +213,12 @@ def _peer_worker(rank, world, port, seed, n, nq, out_path, dtype):
     from multimodal_audio_search_b200.sharded import shard_range
     torch.cuda.set_device(0)
     lo, hi = shard_range(n, rank, world)
-    idx = SegmentIndex(dtype, capacity=hi - lo, device=0)
+    idx = SegmentIndex(dtype.split("+")[0], capacity=hi - lo, device=0)
     idx.append_synth(seed, n, lo, hi, n_queries=nq, plants=60, partial=True)
     idx.row_base = lo
     idx.set_option("gemm_min_queries", 4)          # bf16: batches of >= 4 queries take the tensor-core scan (fused merge too)
+    if dtype.endswith("+shadow"):                  # fp32 shard: batches preselected from bf16 shadows, exact local top-k pushed
+        idx.enable_tensor_core_batches()
     sh = ShardedSearcher(idx, rank, world, exchange="p2p", max_queries=128, max_k=128)
     q = synth.raw_queries(seed, 0, nq)
     qd = torch.from_numpy(q).cuda()
@@ -251,7 +253,7 @@ def _peer_worker(rank, world, port, seed, n, nq, out_path, dtype):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,dtype", [(2, "fp32"), (3, "fp32"), (2, "bf16")])
+@pytest.mark.parametrize("world,dtype", [(2, "fp32"), (3, "fp32"), (2, "bf16"), (2, "fp32+shadow")])
 def test_peer_exchange_two_processes_one_gpu(tmp_path, world, dtype):
     """World of 2 (3) ranks = 2 (3) processes, all on cuda:0, exchange buffers shared through CUDA IPC: the
     finalize kernel's peer stores + epoch flags + merge must give every rank exactly the answer of
@@ -260,7 +262,7 @@ def test_peer_exchange_two_processes_one_gpu(tmp_path, world, dtype):
     torch = pytest.importorskip("torch")
     import torch.multiprocessing as mp
     seed, n, nq = 41, 90_000, 100                    # world = 3, k = 100: 300 candidates per query -> the merge SORTS
-    whole = SegmentIndex(dtype, capacity=n)
+    whole = SegmentIndex(dtype.split("+")[0], capacity=n)
     whole.append_synth(seed, n, 0, n, n_queries=nq, plants=60, partial=True)
     q = synth.raw_queries(seed, 0, nq)
     wa = np.linspace(0.2, 0.8, nq); wb = 1 - wa
@@ -269,7 +271,7 @@ def test_peer_exchange_two_processes_one_gpu(tmp_path, world, dtype):
     want = [whole.search(q[a:b], wa[a:b], wb[a:b], k=k, path="gemv") for a, b, k in cases]
     whole.close()
     out = str(tmp_path / "peer")
-    port = 29500 + (os.getpid() % 2000) + 7 * world + (3 if dtype == "bf16" else 0)      # one rendezvous port per variant
+    port = 29500 + (os.getpid() % 2000) + 7 * world + {"fp32": 0, "bf16": 3, "fp32+shadow": 5}[dtype]   # one rendezvous port per variant
     ctx = mp.spawn(_peer_worker, args=(world, port, seed, n, nq, out, dtype), nprocs=world, join=False)
     deadline = 240
     import time
