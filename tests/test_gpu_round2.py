@@ -246,6 +246,7 @@ def _peer_worker(rank, world, port, seed, n, nq, out_path, dtype):
     for rep in range(2):
         r = sh2.search(q2, 0.5, 0.5, k=10, threshold=-1.0, to_host=True)
         res[f"tiny_i{rep}"], res[f"tiny_f{rep}"], res[f"tiny_c{rep}"] = r.indices, r.fusion, r.count
+    res["shadow_queries"] = np.array([idx.get_option("total_shadow_queries")])
     torch.cuda.synchronize()
     dist.barrier()
     np.savez(out_path + f".{rank}.npz", **res)
@@ -288,6 +289,8 @@ def test_peer_exchange_two_processes_one_gpu(tmp_path, world, dtype):
     assert tiny_want.count[0] >= 1
     for rank in range(world):
         z = np.load(out + f".{rank}.npz")
+        # the fp32 + shadow shards really answered their batches (9, 48 and 100 queries, twice) on the tensor cores
+        assert int(z["shadow_queries"][0]) == (2 * (9 + 48 + 100) if dtype.endswith("+shadow") else 0)
         for rep in range(2):
             np.testing.assert_array_equal(z[f"tiny_i{rep}"], tiny_want.indices, err_msg=f"rank {rank}: empty second shard")
             np.testing.assert_array_equal(z[f"tiny_f{rep}"], tiny_want.fusion)
