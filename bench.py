@@ -630,7 +630,9 @@ def main():
         per, nq, k = 60_000, 40, 10
         n_total = per * world
         exact, within, n, detail = 0, 0, 0, []
-        for dtype in ("fp32", "bf16"):            # bf16 shards: batches of >= 4 queries take the tensor-core scan
+        # bf16 shards: batches of >= 4 queries take the tensor-core scan; fp32+shadow shards: batches are
+        # preselected from bf16 shadows, re-scored exactly and certified locally, then packed and pushed
+        for dtype in ("fp32", "bf16", "fp32+shadow"):
             e_, w_, n_ = cross_check_one(dtype, per, nq, n_total, detail)
             exact, within, n = exact + e_, within + w_, n + n_
         t = torch.tensor([n - exact, n - within], device="cuda")
@@ -639,18 +641,20 @@ def main():
         dist.barrier()
         return {"ok": int(t[1].item()) == 0, "queries": n, "not_bit_identical_over_all_ranks": int(t[0].item()),
                 "outside_tolerance_over_all_ranks": int(t[1].item()), "tolerance": 1e-5, "examples_rank0": detail,
-                "what": f"{world} x {per} segments, fp32 and bf16 (bf16 batches on the tensor cores): ShardedSearcher "
+                "what": f"{world} x {per} segments, fp32, bf16 (batches on the tensor cores) and fp32 with bf16 shadows: ShardedSearcher "
                         f"({exchange_state['kind']}) on every rank vs one index over all rows on the same rank (exact scan); identical "
                         f"indices and float64 fusion scores except swaps between rows closer than the fp32 tolerance at the k-th "
                         f"boundary; fused and separate merge, device and host outputs"}
 
     def cross_check_one(dtype, per, nq, n_total, detail):
-        whole = SegmentIndex(dtype, capacity=n_total, device=local)
+        whole = SegmentIndex(dtype.split("+")[0], capacity=n_total, device=local)
         whole.append_synth(SEED + 1, n_total, 0, n_total, n_queries=nq, plants=30, partial=True)
-        part = SegmentIndex(dtype, capacity=per, device=local)
+        part = SegmentIndex(dtype.split("+")[0], capacity=per, device=local)
         part.append_synth(SEED + 1, n_total, rank * per, (rank + 1) * per, n_queries=nq, plants=30, partial=True)
         part.row_base = rank * per
         part.set_option("gemm_min_queries", 4)
+        if dtype.endswith("+shadow"):
+            part.enable_tensor_core_batches()
         sh = ShardedSearcher(part, rank, world, exchange=exchange_state["kind"], max_queries=64, max_k=100)
         q = synth.raw_queries(SEED + 1, 0, nq)
         qd = torch.from_numpy(q).cuda()
